@@ -1,0 +1,366 @@
+"""Inference engine: request queue, continuous batching over fixed batch slots, paged-KV
+admission control, token streaming.  The reference runs one blocking
+``model.generate`` per request inside the event loop (no batching, no KV management,
+/root/reference/bee2bee/services.py:85-116, api.py:229); here requests are only *enqueued*
+by the asyncio side and a scheduler thread drives the GPU:
+
+    admit (pages available?) -> prefill burst -> decode burst of N graph replays -> read tokens
+    -> EOS / max_new_tokens / stop handling -> free slots -> repeat
+
+Backends: ``GpuRunner`` (hand-written sm_100a kernels; one per GPU, pieces over NVLink) or
+``TorchRunner`` (plain PyTorch; CPU plumbing configuration and numerical oracle).
+"""
+from __future__ import annotations
+
+import itertools
+import queue
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from ..models.config import ModelConfig, resolve_config, split_layers
+from ..models.torch_ref import TorchPiece, sample_reference
+from ..models.weights import load_or_init
+from .kv import PAGE, PageAllocator
+
+
+@dataclass
+class SamplingParams:
+    max_new_tokens: int = 32
+    temperature: float = 0.7
+    top_p: float = 0.95                # reference streaming default (hf.py:103)
+    repetition_penalty: float = 1.15   # reference streaming default (hf.py:95)
+    seed: Optional[int] = None
+    stop_token_ids: Sequence[int] = ()
+    ignore_eos: bool = False
+
+
+@dataclass
+class Request:
+    rid: int
+    prompt_ids: List[int]
+    params: SamplingParams
+    on_token: Optional[Callable[[int], None]] = None
+    out_ids: List[int] = field(default_factory=list)
+    slot: int = -1
+    done: threading.Event = field(default_factory=threading.Event)
+    finish_reason: str = ""
+    error: Optional[str] = None
+    t_submit: float = 0.0
+    t_first: float = 0.0
+    t_done: float = 0.0
+    consumed: int = 0          # tokens already taken from the history ring
+
+    @property
+    def ttft_ms(self) -> float:
+        return (self.t_first - self.t_submit) * 1e3 if self.t_first else 0.0
+
+    def wait(self, timeout: Optional[float] = None) -> "Request":
+        if not self.done.wait(timeout):
+            raise TimeoutError(f"request {self.rid} timed out")
+        if self.error:
+            raise RuntimeError(self.error)
+        return self
+
+
+# =========================================================================== CPU / oracle backend
+class TorchRunner:
+    """Same interface as GpuRunner, plain PyTorch ops, dense per-slot KV.  Optionally a chain of
+    pieces connected by ``hop`` callables (the loopback p2p transport in the CPU config)."""
+
+    def __init__(self, cfg: ModelConfig, model: str = "", pieces: int = 1, device="cpu", dtype=torch.float32,
+                 max_batch: int = 8, seed: int = 0, hop: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None):
+        self.cfg, self.device, self.dtype, self.max_batch = cfg, torch.device(device), dtype, max_batch
+        ranges = split_layers(cfg.n_layers, pieces)
+        self.pieces: List[TorchPiece] = []
+        for i, r in enumerate(ranges):
+            first, last = i == 0, i == len(ranges) - 1
+            t = load_or_init(model, cfg, r, first, last, device=self.device, dtype=dtype, seed=seed)
+            self.pieces.append(TorchPiece(cfg, r, first, last, t))
+        self.hop = hop
+        self.cache: Dict[int, List[dict]] = {}
+        self.state: Dict[int, dict] = {}
+        self.kernel_launches = 0
+        self.hist_len = 1 << 30
+
+    def _forward(self, slot: int, ids: List[int], pos0: int) -> torch.Tensor:
+        x = torch.tensor([ids], device=self.device)
+        positions = torch.arange(pos0, pos0 + len(ids), device=self.device)[None]
+        caches = self.cache.setdefault(slot, [p.new_cache() for p in self.pieces])
+        for i, p in enumerate(self.pieces):
+            x = p.forward(x, positions, caches[i], logits_last_only=True)
+            if self.hop is not None and i + 1 < len(self.pieces):
+                x = self.hop(i, x)
+        return x[0, -1]
+
+    def _sample(self, st: dict, logits: torch.Tensor) -> int:
+        V = self.cfg.vocab_size
+        seen = torch.zeros(1, V, dtype=torch.bool)
+        seen[0, torch.tensor(sorted(st["seen"]), dtype=torch.long)] = True
+        tok = int(sample_reference(logits[None, :V].cpu(), seen, st["temperature"], st["top_p"], st["rep"],
+                                   st["gen"]))
+        st["seen"].add(tok)
+        return tok
+
+    def prefill(self, seqs) -> None:
+        with torch.no_grad():
+            for s in seqs:
+                self.cache.pop(s.slot, None)
+                g = torch.Generator().manual_seed(int(s.seed) & 0x7FFFFFFF)
+                st = dict(temperature=s.temperature, top_p=s.top_p, rep=s.repetition_penalty, gen=g,
+                          seen=set(int(t) for t in s.prompt), pos=len(s.prompt), hist=[])
+                logits = self._forward(s.slot, list(s.prompt), 0)
+                tok = self._sample(st, logits)
+                st["hist"].append(tok)
+                self.state[s.slot] = st
+
+    def decode(self, n_steps: int) -> None:
+        with torch.no_grad():
+            for _ in range(n_steps):
+                for slot, st in self.state.items():
+                    if not st.get("active", True):
+                        continue
+                    logits = self._forward(slot, [st["hist"][-1]], st["pos"])
+                    st["pos"] += 1
+                    st["hist"].append(self._sample(st, logits))
+
+    def sync(self) -> None:
+        pass
+
+    def tokens_of(self, slot: int, start: int, count: int) -> List[int]:
+        return self.state[slot]["hist"][start:start + count]
+
+    def release(self, slots) -> None:
+        for b in slots:
+            self.state.pop(b, None)
+            self.cache.pop(b, None)
+
+    def close(self) -> None:
+        self.state.clear()
+        self.cache.clear()
+
+
+# ============================================================================================ engine
+class Engine:
+    """Scheduler + backend.  Thread-safe ``submit``; ``start()`` spawns the scheduler thread."""
+
+    def __init__(self, model: str = "tiny-llama", cfg: Optional[ModelConfig] = None, device: Optional[str] = None,
+                 pieces: int = 1, max_batch: int = 8, max_seq_len: int = 2048, max_prefill_tokens: int = 2048,
+                 decode_burst: int = 8, seed: int = 0, runner=None, groups: int = 1, rank: int = 0, world: int = 1,
+                 control_group=None):
+        self.model = model
+        self.cfg = cfg or resolve_config(model)
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self.max_batch, self.max_seq_len, self.decode_burst = max_batch, max_seq_len, max(1, decode_burst)
+        self.rank, self.world, self.control_group = rank, world, control_group
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        if runner is not None:
+            self.runner = runner
+        elif self.device.type == "cuda":
+            from .runner import GpuRunner
+            if pieces > 1 and world == 1:
+                raise ValueError("multi-GPU pieces run one process per GPU (SPMD): launch with torchrun and pass "
+                                 "rank/world, see bench.py / bee2bee_b200.parallel.launch")
+            self.runner = GpuRunner(self.cfg, model, rank, world, self.device, max_batch=max_batch, groups=groups,
+                                    max_seq_len=max_seq_len, max_prefill_tokens=max_prefill_tokens, seed=seed,
+                                    control_group=control_group)
+        else:
+            self.runner = TorchRunner(self.cfg, model, pieces=pieces, device=self.device, max_batch=max_batch, seed=seed)
+        self.gpu = self.device.type == "cuda"
+        pages_per_seq = (max_seq_len + PAGE - 1) // PAGE
+        self.alloc = PageAllocator(getattr(self.runner, "num_pages", 1 + max_batch * pages_per_seq))
+        self._ids = itertools.count(1)
+        self._waiting: "queue.Queue[Request]" = queue.Queue()
+        self._pending: List[Request] = []
+        self._running: Dict[int, Request] = {}
+        self._free_slots = list(range(max_batch - 1, -1, -1))
+        self._lock = threading.Lock()
+        self._wake = threading.Event()
+        self._stop = False
+        self._thread: Optional[threading.Thread] = None
+        self.stats = {"requests": 0, "tokens": 0, "prefill_tokens": 0, "steps": 0, "busy_s": 0.0,
+                      "started": time.time()}
+
+    # ------------------------------------------------------------------ public
+    def submit(self, prompt_ids: Sequence[int], params: Optional[SamplingParams] = None,
+               on_token: Optional[Callable[[int], None]] = None) -> Request:
+        params = params or SamplingParams()
+        ids = list(prompt_ids)[-(self.max_seq_len - 1):] or [max(self.cfg.bos_token_id, 0)]
+        budget = self.max_seq_len - len(ids)
+        if params.max_new_tokens > budget:
+            params = SamplingParams(**{**params.__dict__, "max_new_tokens": max(1, budget)})
+        r = Request(next(self._ids), ids, params, on_token, t_submit=time.time())
+        self._waiting.put(r)
+        self._wake.set()
+        return r
+
+    def generate(self, prompts: Sequence[Sequence[int]], params: Optional[SamplingParams] = None) -> List[List[int]]:
+        """Blocking helper: run to completion (drives the scheduler inline if no thread is running)."""
+        reqs = [self.submit(p, params) for p in prompts]
+        if self._thread is None:
+            while not all(r.done.is_set() for r in reqs):
+                self.step()
+        return [r.wait().out_ids for r in reqs]
+
+    def start(self) -> None:
+        if self._thread is None:
+            self._stop = False
+            self._thread = threading.Thread(target=self._loop, name="b2b-engine", daemon=True)
+            self._thread.start()
+
+    def stop(self) -> None:
+        self._stop = True
+        self._wake.set()
+        if self._thread is not None:
+            self._thread.join(timeout=10)
+            self._thread = None
+
+    def close(self) -> None:
+        self.stop()
+        self.runner.close()
+
+    def metrics(self) -> Dict[str, float]:
+        up = max(1e-9, time.time() - self.stats["started"])
+        busy = max(1e-9, self.stats["busy_s"])
+        return {"requests": self.stats["requests"], "tokens_generated": self.stats["tokens"],
+                "prefill_tokens": self.stats["prefill_tokens"], "decode_steps": self.stats["steps"],
+                "tokens_per_s": self.stats["tokens"] / busy, "running": len(self._running),
+                "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
+                "uptime_s": up}
+
+    # --------------------------------------------------------------- scheduler
+    def _loop(self) -> None:
+        while not self._stop:
+            try:
+                worked = self.step()
+            except Exception as e:  # keep serving: fail the in-flight requests, not the node
+                worked = True
+                self._fail_all(f"engine error: {e!r}")
+            if not worked:
+                self._wake.wait(0.05)
+                self._wake.clear()
+
+    def _fail_all(self, msg: str) -> None:
+        for r in list(self._running.values()) + self._pending:
+            r.error = msg
+            r.done.set()
+        try:
+            self.runner.release(list(self._running.keys()))
+        except Exception:
+            pass
+        for b in self._running:
+            self.alloc.release(b)
+            self._free_slots.append(b)
+        self._running.clear()
+        self._pending.clear()
+
+    def step(self) -> bool:
+        """One scheduler iteration: admit + prefill, then one decode burst. Returns False when idle."""
+        from .runner import SeqInit
+
+        t0 = time.time()
+        while True:
+            try:
+                self._pending.append(self._waiting.get_nowait())
+            except queue.Empty:
+                break
+        admitted: List[Request] = []
+        still: List[Request] = []
+        for r in self._pending:
+            need = len(r.prompt_ids) + r.params.max_new_tokens
+            if self._free_slots and self.alloc.can_allocate(need):
+                r.slot = self._free_slots.pop()
+                self.alloc.allocate(r.slot, need)
+                admitted.append(r)
+            else:
+                still.append(r)
+        self._pending = still
+        if admitted:
+            seqs = [SeqInit(slot=r.slot, prompt=r.prompt_ids, pages=self.alloc.owned(r.slot),
+                            temperature=r.params.temperature, top_p=r.params.top_p,
+                            repetition_penalty=r.params.repetition_penalty,
+                            seed=r.params.seed if r.params.seed is not None else (r.rid * 2654435761) & 0x7FFFFFFF)
+                    for r in admitted]
+            self.runner.prefill(seqs)
+            for r in admitted:
+                self._running[r.slot] = r
+                self.stats["prefill_tokens"] += len(r.prompt_ids)
+                self.stats["requests"] += 1
+            self._collect(first=True)
+        if not self._running:
+            if admitted:
+                self.stats["busy_s"] += time.time() - t0
+            return bool(admitted)
+        remaining = min(r.params.max_new_tokens - len(r.out_ids) for r in self._running.values())
+        n = max(1, min(self.decode_burst, remaining))
+        self.runner.decode(n)
+        self.runner.sync()
+        self.stats["steps"] += n
+        self._collect(steps=n)
+        self.stats["busy_s"] += time.time() - t0
+        return True
+
+    def _fetch_window(self, width: int) -> torch.Tensor:
+        """[max_batch, width] newest tokens of every slot, starting at each request's read cursor.
+        On a multi-rank mesh the ring lives on rank 0 and the window is broadcast so that every rank
+        takes identical scheduling decisions (replicated control plane)."""
+        dev = self.device
+        cur = torch.zeros(self.max_batch, dtype=torch.int64)
+        for b, r in self._running.items():
+            cur[b] = r.consumed
+        idx = (cur[:, None] + torch.arange(width)[None, :]).clamp_(max=self.runner.hist_len - 1).to(dev)
+        self.h2d_bytes += idx.numel() * 8
+        if self.rank == 0:
+            win = self.runner.history.long().gather(1, idx).int()
+        else:
+            win = torch.zeros((self.max_batch, width), device=dev, dtype=torch.int32)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(win, src=0, group=self.control_group)
+        self.d2h_bytes += win.numel() * 4
+        return win.cpu()
+
+    def _collect(self, first: bool = False, steps: int = 0) -> None:
+        """Pull freshly produced tokens for every running request, stream them, retire finished ones."""
+        width = 1 if first else steps
+        if self.gpu:
+            win = self._fetch_window(width)
+        finished: List[int] = []
+        for b, r in list(self._running.items()):
+            have = 1 if first and r.consumed == 0 else steps
+            if first and r.consumed > 0:
+                continue
+            new = (win[b, :have].tolist() if self.gpu else self.runner.tokens_of(b, r.consumed, have))
+            r.consumed += len(new)
+            for tok in new:
+                if r.finish_reason:
+                    break
+                if not r.t_first:
+                    r.t_first = time.time()
+                r.out_ids.append(int(tok))
+                self.stats["tokens"] += 1
+                if r.on_token is not None:
+                    try:
+                        r.on_token(int(tok))
+                    except Exception:
+                        pass
+                if (not r.params.ignore_eos and int(tok) == self.cfg.eos_token_id) or int(tok) in r.params.stop_token_ids:
+                    r.finish_reason = "stop"
+                elif len(r.out_ids) >= r.params.max_new_tokens:
+                    r.finish_reason = "length"
+            if r.finish_reason:
+                finished.append(b)
+        if finished:
+            self.runner.release(finished)
+            for b in finished:
+                r = self._running.pop(b)
+                self.alloc.release(b)
+                self._free_slots.append(b)
+                r.t_done = time.time()
+                r.done.set()

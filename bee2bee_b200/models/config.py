@@ -1,0 +1,224 @@
+"""Model architecture descriptions for the decoder families the mesh serves.
+
+The reference ships no model configs (it defers to ``transformers``,
+/root/reference/bee2bee/hf.py:23-32); these presets are the public architectures named in
+BASELINE.json (distilgpt2, Llama-3-8B, Zephyr-7B-beta = Mistral-7B, gemma-2-2b) plus tiny
+variants of each family for tests.  A config can also be read from a Hugging Face
+``config.json`` (``ModelConfig.from_hf_dict``) so ``serve-hf --model <local dir>`` works.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import asdict, dataclass, field
+from typing import Dict, List, Optional
+
+
+@dataclass
+class ModelConfig:
+    name: str = "tiny-llama"
+    family: str = "llama"            # gpt2 | llama | mistral | gemma2
+    vocab_size: int = 512
+    hidden_size: int = 256
+    n_layers: int = 2
+    n_heads: int = 2
+    n_kv_heads: int = 1
+    head_dim: int = 128
+    ffn_size: int = 512
+    max_position: int = 8192
+    norm: str = "rms"                # rms | ln
+    norm_eps: float = 1e-5
+    act: str = "silu"                # silu | gelu_tanh
+    glu: bool = True
+    rope_theta: float = 10000.0      # <= 0: learned absolute positions (GPT-2)
+    tie_embeddings: bool = False
+    bias: bool = False               # GPT-2 style biases on every linear
+    sliding_window: int = 0          # 0 = full attention
+    window_pattern: str = "all"      # all | alternate (Gemma-2: even layers are local)
+    attn_softcap: float = 0.0
+    final_softcap: float = 0.0
+    query_scale: float = 0.0         # 0 -> 1/sqrt(head_dim); Gemma-2: query_pre_attn_scalar ** -0.5
+    post_norms: bool = False         # Gemma-2 post-attention / post-FFN norms
+    gemma_norm: bool = False         # RMSNorm weight stored as (w - 1)
+    embed_scale: float = 1.0         # Gemma: sqrt(hidden)
+    eos_token_id: int = -1
+    bos_token_id: int = -1
+
+    # ------------------------------------------------------------------ derived
+    @property
+    def q_dim(self) -> int:
+        return self.n_heads * self.head_dim
+
+    @property
+    def kv_dim(self) -> int:
+        return self.n_kv_heads * self.head_dim
+
+    @property
+    def softmax_scale(self) -> float:
+        return self.query_scale if self.query_scale > 0 else 1.0 / math.sqrt(self.head_dim)
+
+    def layer_window(self, layer: int) -> int:
+        if self.sliding_window <= 0:
+            return 0
+        if self.window_pattern == "alternate":
+            return self.sliding_window if layer % 2 == 0 else 0
+        return self.sliding_window
+
+    def param_count(self) -> int:
+        h, f = self.hidden_size, self.ffn_size
+        per = h * (self.q_dim + 2 * self.kv_dim) + self.q_dim * h + (3 if self.glu else 2) * h * f
+        emb = self.vocab_size * h * (1 if self.tie_embeddings else 2)
+        return self.n_layers * per + emb
+
+    def to_dict(self) -> Dict:
+        return asdict(self)
+
+    # --------------------------------------------------------------- HF interop
+    @staticmethod
+    def from_hf_dict(d: Dict, name: str = "") -> "ModelConfig":
+        mt = d.get("model_type", "llama")
+        if mt == "gpt2":
+            h = d.get("n_embd", 768)
+            nh = d.get("n_head", 12)
+            return ModelConfig(
+                name=name or "gpt2", family="gpt2", vocab_size=d.get("vocab_size", 50257), hidden_size=h,
+                n_layers=d.get("n_layer", 12), n_heads=nh, n_kv_heads=nh, head_dim=h // nh,
+                ffn_size=d.get("n_inner") or 4 * h, max_position=d.get("n_positions", 1024), norm="ln",
+                norm_eps=d.get("layer_norm_epsilon", 1e-5), act="gelu_tanh", glu=False, rope_theta=0.0,
+                tie_embeddings=True, bias=True, eos_token_id=d.get("eos_token_id", 50256),
+                bos_token_id=d.get("bos_token_id", 50256))
+        h = d["hidden_size"]
+        nh = d["num_attention_heads"]
+        hd = d.get("head_dim") or h // nh
+        common = dict(
+            name=name or mt, vocab_size=d["vocab_size"], hidden_size=h, n_layers=d["num_hidden_layers"], n_heads=nh,
+            n_kv_heads=d.get("num_key_value_heads", nh), head_dim=hd, ffn_size=d["intermediate_size"],
+            max_position=d.get("max_position_embeddings", 8192), norm="rms", norm_eps=d.get("rms_norm_eps", 1e-5),
+            rope_theta=float(d.get("rope_theta", 10000.0)), tie_embeddings=bool(d.get("tie_word_embeddings", False)),
+            eos_token_id=_first_int(d.get("eos_token_id", -1)), bos_token_id=_first_int(d.get("bos_token_id", -1)))
+        if mt == "gemma2":
+            return ModelConfig(
+                family="gemma2", act="gelu_tanh", glu=True, sliding_window=d.get("sliding_window", 4096),
+                window_pattern="alternate", attn_softcap=float(d.get("attn_logit_softcapping") or 0.0),
+                final_softcap=float(d.get("final_logit_softcapping") or 0.0),
+                query_scale=float(d.get("query_pre_attn_scalar", hd)) ** -0.5, post_norms=True, gemma_norm=True,
+                embed_scale=math.sqrt(h), **{**common, "tie_embeddings": True})
+        if mt == "mistral":
+            return ModelConfig(family="mistral", act="silu", glu=True, sliding_window=d.get("sliding_window") or 0,
+                               **common)
+        return ModelConfig(family="llama", act="silu", glu=True, **common)
+
+    def to_hf_dict(self) -> Dict:
+        """A ``config.json`` that ``transformers`` accepts for this architecture."""
+        if self.family == "gpt2":
+            return {"model_type": "gpt2", "architectures": ["GPT2LMHeadModel"], "vocab_size": self.vocab_size,
+                    "n_embd": self.hidden_size, "n_layer": self.n_layers, "n_head": self.n_heads,
+                    "n_positions": self.max_position, "n_ctx": self.max_position, "n_inner": self.ffn_size,
+                    "activation_function": "gelu_new", "layer_norm_epsilon": self.norm_eps,
+                    "bos_token_id": self.bos_token_id, "eos_token_id": self.eos_token_id,
+                    "resid_pdrop": 0.0, "embd_pdrop": 0.0, "attn_pdrop": 0.0}
+        base = {"vocab_size": self.vocab_size, "hidden_size": self.hidden_size,
+                "num_hidden_layers": self.n_layers, "num_attention_heads": self.n_heads,
+                "num_key_value_heads": self.n_kv_heads, "head_dim": self.head_dim,
+                "intermediate_size": self.ffn_size, "max_position_embeddings": self.max_position,
+                "rms_norm_eps": self.norm_eps, "rope_theta": self.rope_theta,
+                "tie_word_embeddings": self.tie_embeddings, "bos_token_id": self.bos_token_id,
+                "eos_token_id": self.eos_token_id, "attention_bias": False, "mlp_bias": False,
+                "attention_dropout": 0.0}
+        if self.family == "gemma2":
+            base.update({"model_type": "gemma2", "architectures": ["Gemma2ForCausalLM"],
+                         "hidden_activation": "gelu_pytorch_tanh", "sliding_window": self.sliding_window,
+                         "attn_logit_softcapping": self.attn_softcap or None,
+                         "final_logit_softcapping": self.final_softcap or None,
+                         "query_pre_attn_scalar": round(self.softmax_scale ** -2)})
+        elif self.family == "mistral":
+            base.update({"model_type": "mistral", "architectures": ["MistralForCausalLM"], "hidden_act": "silu",
+                         "sliding_window": self.sliding_window or None})
+        else:
+            base.update({"model_type": "llama", "architectures": ["LlamaForCausalLM"], "hidden_act": "silu"})
+        return base
+
+
+def _first_int(v) -> int:
+    if isinstance(v, (list, tuple)):
+        return int(v[0]) if v else -1
+    return -1 if v is None else int(v)
+
+
+def _gpt2(name, layers, hidden, heads):
+    return ModelConfig(name=name, family="gpt2", vocab_size=50257, hidden_size=hidden, n_layers=layers, n_heads=heads,
+                       n_kv_heads=heads, head_dim=hidden // heads, ffn_size=4 * hidden, max_position=1024, norm="ln",
+                       norm_eps=1e-5, act="gelu_tanh", glu=False, rope_theta=0.0, tie_embeddings=True, bias=True,
+                       eos_token_id=50256, bos_token_id=50256)
+
+
+PRESETS: Dict[str, ModelConfig] = {
+    "distilgpt2": _gpt2("distilgpt2", 6, 768, 12),
+    "gpt2": _gpt2("gpt2", 12, 768, 12),
+    "llama-3-8b": ModelConfig(name="llama-3-8b", family="llama", vocab_size=128256, hidden_size=4096, n_layers=32,
+                              n_heads=32, n_kv_heads=8, head_dim=128, ffn_size=14336, max_position=8192,
+                              norm_eps=1e-5, rope_theta=500000.0, eos_token_id=128001, bos_token_id=128000),
+    "zephyr-7b-beta": ModelConfig(name="zephyr-7b-beta", family="mistral", vocab_size=32000, hidden_size=4096,
+                                  n_layers=32, n_heads=32, n_kv_heads=8, head_dim=128, ffn_size=14336,
+                                  max_position=32768, norm_eps=1e-5, rope_theta=10000.0, sliding_window=4096,
+                                  eos_token_id=2, bos_token_id=1),
+    "gemma-2-2b": ModelConfig(name="gemma-2-2b", family="gemma2", vocab_size=256000, hidden_size=2304, n_layers=26,
+                              n_heads=8, n_kv_heads=4, head_dim=256, ffn_size=9216, max_position=8192,
+                              norm_eps=1e-6, act="gelu_tanh", rope_theta=10000.0, tie_embeddings=True,
+                              sliding_window=4096, window_pattern="alternate", attn_softcap=50.0, final_softcap=30.0,
+                              query_scale=256 ** -0.5, post_norms=True, gemma_norm=True,
+                              embed_scale=math.sqrt(2304), eos_token_id=1, bos_token_id=2),
+    # tiny variants (tests / smoke): same code paths, kernel-friendly shapes
+    "tiny-llama": ModelConfig(name="tiny-llama", family="llama", vocab_size=512, hidden_size=256, n_layers=4,
+                              n_heads=4, n_kv_heads=2, head_dim=128, ffn_size=512, rope_theta=500000.0,
+                              eos_token_id=1, bos_token_id=0),
+    "tiny-mistral": ModelConfig(name="tiny-mistral", family="mistral", vocab_size=512, hidden_size=256, n_layers=4,
+                                n_heads=4, n_kv_heads=2, head_dim=128, ffn_size=512, sliding_window=96,
+                                eos_token_id=1, bos_token_id=0),
+    "tiny-gemma2": ModelConfig(name="tiny-gemma2", family="gemma2", vocab_size=512, hidden_size=256, n_layers=4,
+                               n_heads=2, n_kv_heads=1, head_dim=256, ffn_size=512, norm_eps=1e-6, act="gelu_tanh",
+                               tie_embeddings=True, sliding_window=96, window_pattern="alternate", attn_softcap=50.0,
+                               final_softcap=30.0, query_scale=256 ** -0.5, post_norms=True, gemma_norm=True,
+                               embed_scale=16.0, eos_token_id=1, bos_token_id=0),
+    "tiny-gpt2": _gpt2("tiny-gpt2", 4, 128, 2),
+}
+PRESETS["tiny-gpt2"].vocab_size = 384
+PRESETS["tiny-gpt2"].eos_token_id = 1
+PRESETS["tiny-gpt2"].bos_token_id = 0
+
+ALIASES = {
+    "meta-llama/meta-llama-3-8b": "llama-3-8b", "meta-llama/llama-3-8b": "llama-3-8b", "llama3": "llama-3-8b",
+    "llama-3-8b-instruct": "llama-3-8b", "huggingfaceh4/zephyr-7b-beta": "zephyr-7b-beta",
+    "zephyr": "zephyr-7b-beta", "mistral-7b": "zephyr-7b-beta", "google/gemma-2-2b": "gemma-2-2b",
+    "gemma2:2b": "gemma-2-2b", "gemma2": "gemma-2-2b", "distilbert/distilgpt2": "distilgpt2",
+    "openai-community/gpt2": "gpt2",
+}
+
+
+def resolve_config(model: str) -> ModelConfig:
+    """Preset name, alias, or a local directory containing ``config.json``."""
+    if os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):
+        with open(os.path.join(model, "config.json")) as f:
+            return ModelConfig.from_hf_dict(json.load(f), name=os.path.basename(os.path.normpath(model)))
+    key = model.lower()
+    key = ALIASES.get(key, key)
+    if key in PRESETS:
+        return PRESETS[key]
+    tail = key.split("/")[-1]
+    tail = ALIASES.get(tail, tail)
+    if tail in PRESETS:
+        return PRESETS[tail]
+    raise KeyError(f"unknown model '{model}' (presets: {sorted(PRESETS)})")
+
+
+def split_layers(n_layers: int, pieces: int) -> List[range]:
+    """Contiguous layer ranges, earlier pieces take the remainder (26 over 4 -> 7/7/6/6)."""
+    pieces = max(1, min(pieces, n_layers))
+    base, rem = divmod(n_layers, pieces)
+    out, start = [], 0
+    for i in range(pieces):
+        n = base + (1 if i < rem else 0)
+        out.append(range(start, start + n))
+        start += n
+    return out

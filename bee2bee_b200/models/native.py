@@ -1,0 +1,261 @@
+"""One *piece* (contiguous layer range) resident on one B200, executed entirely by the
+hand-written sm_100a kernels in ``csrc/``.
+
+Per decoder layer (Llama / Mistral) exactly five launches, all on one stream:
+
+    QKV GEMM  [fused: RMSNorm(x) via folded gamma + in-kernel 1/rms, RoPE, paged-KV append]
+    attention [paged KV, GQA]
+    O GEMM    [fused: + residual]
+    gate/up   [fused: RMSNorm, SwiGLU]
+    down GEMM [fused: + residual]   <- on the last layer of a piece its epilogue stores the
+                                       tiles into the NEXT piece's input buffer on the peer
+                                       GPU over NVLink and publishes a release flag
+
+and the first GEMM of the next piece acquires that flag after prefetching its weights.
+Gemma-2 adds its post-norms as residual-fused RMSNorm kernels; GPT-2 uses LayerNorm +
+bias/GELU epilogues.  Replaces ``build_distilbert_partial`` + the JSON hidden-state hop
+of the reference (/root/reference/bee2bee/hf.py:180-205, bee2bee/node.py:249-277).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from .. import ops
+from .config import ModelConfig
+from .weights import Tensors
+
+
+@dataclass
+class Handoff:
+    """Raw device addresses of one micro-batch slot's handoff endpoints (0 = not used).
+
+    ``in_*`` live in THIS rank's memory (written by the upstream peer); ``out_*`` are the
+    downstream peer's ``in_*`` mapped through CUDA IPC / peer access.  For piece 0 the
+    "input" is the sampled-token buffer written by the last piece; for the last piece the
+    "output" is that token buffer on piece 0."""
+    in_x: int = 0            # [max_tokens, H] bf16 staging buffer (local); piece 0: int32 token buffer
+    in_flag: int = 0         # u32: upstream publishes its epoch here (local)
+    in_epoch: int = 0        # u32: number of inputs already consumed (local)
+    up_ack: int = 0          # u32 on the upstream rank: its out_free for our input slot
+    out_x: int = 0           # downstream staging buffer (peer); last piece: piece 0's token buffer
+    out_flag: int = 0        # downstream in_flag (peer)
+    out_epoch: int = 0       # u32: number of outputs already published (local)
+    out_free: int = 0        # u32: downstream acks land here (local)
+    done: int = 0            # u32 scratch counter (local)
+
+
+@dataclass
+class BatchMeta:
+    """Device-resident description of the tokens of one forward call."""
+    ids: torch.Tensor          # [T] int32 (piece 0)
+    positions: torch.Tensor    # [T] int32
+    slots: torch.Tensor        # [T] int32 physical KV slot (-1 = do not store)
+    q_start: torch.Tensor      # [S] int32
+    q_len: torch.Tensor        # [S] int32
+    kv_len: torch.Tensor       # [S] int32
+    block_table: torch.Tensor  # [S, max_pages] int32
+    n_tokens: int
+    n_seqs: int
+    max_q: int
+    last_idx: Optional[torch.Tensor] = None   # [S] int64 row of each sequence's last token (prefill)
+    splits: int = 1
+
+
+class NativePiece:
+    def __init__(self, cfg: ModelConfig, layers: Iterable[int], first: bool, last: bool, tensors: Tensors,
+                 device: torch.device, max_tokens: int, max_seqs: int, num_pages: int):
+        self.cfg, self.layers, self.first, self.last = cfg, list(layers), first, last
+        self.device = torch.device(device)
+        self.max_tokens, self.max_seqs, self.num_pages = max_tokens, max_seqs, num_pages
+        self.fused_norm = cfg.norm == "rms"
+        c = cfg
+        assert c.hidden_size % 128 == 0 or c.hidden_size % 64 == 0, "hidden must be a multiple of 64"
+        bf = torch.bfloat16
+        dev = self.device
+        t = {k: v.to(device=dev, dtype=bf) for k, v in tensors.items()}
+        self.w: Dict[str, torch.Tensor] = {}
+        for l in self.layers:
+            p = f"l{l}."
+            wq, wk, wv = t[p + "wq"], t[p + "wk"], t[p + "wv"]
+            if c.rope_theta > 0:
+                wq = ops.rope_interleave_rows(wq, c.n_heads, c.head_dim)
+                wk = ops.rope_interleave_rows(wk, c.n_kv_heads, c.head_dim)
+            wqkv = torch.cat([wq, wk, wv], 0)
+            if self.fused_norm:
+                wqkv = ops.fold_gamma(wqkv, t[p + "ln1_w"], c.gemma_norm)
+            self.w[p + "wqkv"] = wqkv.contiguous()
+            self.w[p + "wo"] = t[p + "wo"].contiguous()
+            if c.glu:
+                wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
+                if self.fused_norm:
+                    wgu = ops.fold_gamma(wgu, t[p + "ln2_w"], c.gemma_norm)
+                self.w[p + "wgu"] = wgu
+            else:
+                self.w[p + "w_up"] = t[p + "w_up"].contiguous()
+            self.w[p + "w_down"] = t[p + "w_down"].contiguous()
+            if not self.fused_norm:
+                for n in ("ln1_w", "ln1_b", "ln2_w", "ln2_b"):
+                    self.w[p + n] = t[p + n]
+            if c.bias:
+                self.w[p + "bqkv"] = torch.cat([t[p + "bq"], t[p + "bk"], t[p + "bv"]]).float().contiguous()
+                for n in ("bo", "b_up", "b_down"):
+                    self.w[p + n] = t[p + n].float().contiguous()
+            if c.post_norms:
+                self.w[p + "post_attn_w"] = t[p + "post_attn_w"]
+                self.w[p + "post_ffn_w"] = t[p + "post_ffn_w"]
+        if first:
+            self.w["embed"] = t["embed"].contiguous()
+            if c.rope_theta <= 0:
+                self.w["pos_embed"] = t["pos_embed"].contiguous()
+        if last:
+            head = t["embed"] if c.tie_embeddings else t["lm_head"]
+            if self.fused_norm:
+                head = ops.fold_gamma(head, t["final_norm_w"], c.gemma_norm)
+            else:
+                self.w["final_norm_w"], self.w["final_norm_b"] = t["final_norm_w"], t["final_norm_b"]
+            self.w["lm_head"] = ops.pad_rows(head, 128)
+            self.vocab_pad = self.w["lm_head"].shape[0]
+        del t
+
+        # ---- KV cache: one [pages, 64, n_kv, D] pair per layer
+        self.k_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
+                        for l in self.layers}
+        self.v_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
+                        for l in self.layers}
+        # ---- activations
+        H = c.hidden_size
+        self.xa = torch.zeros((max_tokens, H), device=dev, dtype=bf)
+        self.xb = torch.zeros((max_tokens, H), device=dev, dtype=bf)
+        self.q_buf = torch.zeros((max_tokens, c.q_dim), device=dev, dtype=bf)
+        self.attn_buf = torch.zeros((max_tokens, c.q_dim), device=dev, dtype=bf)
+        self.h_buf = torch.zeros((max_tokens, c.ffn_size), device=dev, dtype=bf)
+        if not self.fused_norm or c.post_norms:
+            self.n_buf = torch.zeros((max_tokens, H), device=dev, dtype=bf)
+        if not self.fused_norm:
+            self.qkv_buf = torch.zeros((max_tokens, c.q_dim + 2 * c.kv_dim), device=dev, dtype=bf)
+        if last:
+            self.last_x = torch.zeros((max_seqs, H), device=dev, dtype=bf)
+            self.logits = torch.zeros((max_seqs, self.vocab_pad), device=dev, dtype=torch.float32)
+        self.max_splits = 16
+        g = c.n_heads // c.n_kv_heads
+        rows = max(4, (g + 3) // 4 * 4)
+        self.attn_ws = torch.zeros(max_seqs * c.n_kv_heads * self.max_splits * rows * (c.head_dim + 2), device=dev,
+                                   dtype=torch.float32)
+
+    # ------------------------------------------------------------------ helpers
+    def weight_bytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.w.values())
+
+    def _use_inline_rstd(self, T: int) -> bool:
+        return T <= 64
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, m: BatchMeta, x_in: Optional[torch.Tensor] = None, hand: Optional[Handoff] = None,
+                out_x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Runs the piece for the tokens described by ``m``.
+
+        first piece: embeds ``m.ids``; otherwise reads ``x_in`` ([T, H], may be the peer-written
+        staging buffer, guarded by ``hand.in_flag``).  Non-last piece: returns (and, with a
+        handoff, peer-stores) the hidden states.  Last piece: returns fp32 logits [S, vocab_pad]."""
+        c, T = self.cfg, m.n_tokens
+        hand = hand or Handoff()
+        eps = c.norm_eps
+        if self.first:
+            x = self.xa[:T]
+            ops.embed(m.ids, self.w["embed"], x, pos_table=self.w.get("pos_embed"),
+                      positions=m.positions if c.rope_theta <= 0 else None,
+                      scale=float(torch.tensor(c.embed_scale, dtype=torch.bfloat16)) if c.embed_scale != 1.0 else 1.0,
+                      tok_flag=hand.in_flag, tok_epoch=hand.in_epoch if hand.in_flag else 0)
+            wait_flag = wait_epoch = 0
+        else:
+            x = x_in[:T]
+            wait_flag, wait_epoch = hand.in_flag, hand.in_epoch
+        inline = self._use_inline_rstd(T)
+        n_layers = len(self.layers)
+        for li, l in enumerate(self.layers):
+            p = f"l{l}."
+            is_tail = (li == n_layers - 1) and not self.last
+            x2 = self.xb[:T]
+            xn = self.xa[:T]            # layer output buffer (local)
+            # ---------------- attention block
+            if self.fused_norm:
+                r = None if inline else ops.rstd(x, eps)
+                ops.gemm(self.w[p + "wqkv"], x, epi=ops.EPI_QKV_ROPE, rstd=r, norm_from_x=inline, eps=eps,
+                         q_out=self.q_buf, k_cache=self.k_cache[l], v_cache=self.v_cache[l], positions=m.positions,
+                         slots=m.slots, n_q_heads=c.n_heads, n_kv_heads=c.n_kv_heads, head_dim=c.head_dim,
+                         rope_theta=c.rope_theta, q_scale=c.softmax_scale,
+                         wait_flag=wait_flag if li == 0 else 0, wait_epoch=wait_epoch if li == 0 else 0)
+            else:
+                if li == 0 and wait_flag:
+                    ops.native().flag_wait(wait_flag, wait_epoch, 1)
+                n = ops.layernorm(x, self.w[p + "ln1_w"], self.w[p + "ln1_b"], self.n_buf[:T], eps)
+                ops.gemm(self.w[p + "wqkv"], n, out=self.qkv_buf[:T], epi=ops.EPI_PLAIN, bias=self.w.get(p + "bqkv"))
+                ops.kv_append(self.qkv_buf[:T], self.q_buf, self.k_cache[l], self.v_cache[l], m.slots, c.q_dim,
+                              c.kv_dim, c.softmax_scale)
+            ops.attention(self.q_buf, self.k_cache[l], self.v_cache[l], self.attn_buf, m.block_table, m.q_start,
+                          m.q_len, m.kv_len, max_q=m.max_q, n_q=c.n_heads, n_kv=c.n_kv_heads, head_dim=c.head_dim,
+                          window=c.layer_window(l), softcap=c.attn_softcap, splits=m.splits, ws=self.attn_ws)
+            a = self.attn_buf[:T]
+            if c.post_norms:
+                o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
+                ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
+            else:
+                ops.gemm(self.w[p + "wo"], a, out=x2, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"))
+            # ---------------- MLP block
+            tail_kw = {}
+            if is_tail and hand.out_x:
+                tail_kw = dict(out_ptr=hand.out_x, ld_out=c.hidden_size, signal_flag=hand.out_flag,
+                               signal_epoch=hand.out_epoch, done_counter=hand.done, free_flag=hand.out_free,
+                               bump_epoch=hand.in_epoch, ack_flag=hand.up_ack)
+            elif is_tail and out_x is not None:
+                tail_kw = dict(out_ptr=out_x.data_ptr(), ld_out=c.hidden_size)
+            if c.glu:
+                r2 = None
+                if self.fused_norm and not inline:
+                    r2 = ops.rstd(x2, eps)
+                hmid = ops.gemm(self.w[p + "wgu"], x2, out=self.h_buf[:T], epi=ops.EPI_GLU, rstd=r2,
+                                norm_from_x=inline and self.fused_norm, eps=eps, act_gelu=(c.act == "gelu_tanh"))
+            else:
+                n2 = ops.layernorm(x2, self.w[p + "ln2_w"], self.w[p + "ln2_b"], self.n_buf[:T], eps)
+                hmid = ops.gemm(self.w[p + "w_up"], n2, out=self.h_buf[:T], epi=ops.EPI_GELU, bias=self.w.get(p + "b_up"))
+            if c.post_norms:
+                d = ops.gemm(self.w[p + "w_down"], hmid, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
+                if is_tail and hand.out_x:
+                    dst = ops.native().tensor_from_ptr(hand.out_x, [T, c.hidden_size], "bf16", self.device.index)
+                    if hand.out_free:
+                        ops.native().flag_wait(hand.out_free, hand.out_epoch, 0)    # back-pressure
+                    ops.rmsnorm(d, self.w[p + "post_ffn_w"], out=dst, residual=x2, eps=eps, plus_one=c.gemma_norm)
+                    ops.native().flag_signal(hand.out_flag, hand.out_epoch, hand.in_epoch, hand.up_ack)
+                    xn = dst
+                else:
+                    tgt = out_x[:T] if (is_tail and out_x is not None) else xn
+                    ops.rmsnorm(d, self.w[p + "post_ffn_w"], out=tgt, residual=x2, eps=eps, plus_one=c.gemma_norm)
+                    xn = tgt
+            else:
+                ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL, residual=x2,
+                         bias=self.w.get(p + "b_down"), **tail_kw)
+                if tail_kw and out_x is not None and not hand.out_x:
+                    xn = out_x[:T]
+            x = xn
+        if not self.last:
+            return x
+        # ---------------- head: last-token gather, final norm fused into the lm_head GEMM
+        S = m.n_seqs
+        if m.last_idx is not None:
+            torch.index_select(x, 0, m.last_idx, out=self.last_x[:S])
+            xl = self.last_x[:S]
+        else:
+            xl = x[:S]
+        if not self.first and hand.in_flag:
+            # the head GEMM of this piece consumed the input slot; release it to the upstream piece
+            ops.native().flag_signal(0, 0, hand.in_epoch, hand.up_ack)
+        if self.fused_norm:
+            ops.gemm(self.w["lm_head"], xl, out=self.logits[:S], epi=ops.EPI_PLAIN, norm_from_x=True, eps=eps,
+                     out_fp32=True, bn=ops.pick_bn(S))
+        else:
+            n = ops.layernorm(xl, self.w["final_norm_w"], self.w["final_norm_b"], self.n_buf[:S], eps)
+            ops.gemm(self.w["lm_head"], n, out=self.logits[:S], epi=ops.EPI_PLAIN, out_fp32=True)
+        return self.logits[:S]

@@ -1,0 +1,192 @@
+"""Python face of the hand-written sm_100a kernels (``csrc/*.cu`` -> ``bee2bee_b200/_C``).
+
+Every function here launches a native kernel on the current CUDA stream.  There is no
+silent PyTorch fallback on a GPU box: if the extension is missing, ``native()`` raises.
+(The CPU execution backend is ``bee2bee_b200.models.torch_ref`` and is selected explicitly
+by device, never by an import failure.)
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+from typing import Optional
+
+import torch
+
+EPI_PLAIN, EPI_RESIDUAL, EPI_GLU, EPI_QKV_ROPE, EPI_GELU = 0, 1, 2, 3, 4
+PAGE = 64           # tokens per KV page (csrc/attention.cu)
+NUM_SMS = 148
+
+_C = None
+
+
+def native():
+    """The compiled extension module; built in-tree by ``__graft_entry__.build()``."""
+    global _C
+    if _C is None:
+        try:
+            _C = importlib.import_module("bee2bee_b200._C")
+        except ImportError as e:  # pragma: no cover - exercised only on broken installs
+            raise RuntimeError(
+                "bee2bee_b200 native extension is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"at the repo root (import error: {e})") from e
+    return _C
+
+
+def has_native() -> bool:
+    try:
+        native()
+        return True
+    except RuntimeError:
+        return False
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------ weight prep
+def rope_interleave_rows(w: torch.Tensor, n_heads: int, head_dim: int) -> torch.Tensor:
+    """Row permutation inside each head: new row 2j <- old j, 2j+1 <- old j + D/2, so a rotary
+    pair sits in adjacent TMEM lanes of the QKV GEMM epilogue.  q.k dot products are invariant
+    under the (shared) permutation, so attention is unchanged."""
+    half = head_dim // 2
+    idx = torch.arange(head_dim, device=w.device).view(2, half).t().reshape(-1)   # [0, half, 1, half+1, ...]
+    wv = w.view(n_heads, head_dim, *w.shape[1:])
+    return wv[:, idx].reshape(w.shape).contiguous()
+
+
+def glu_interleave_rows(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
+    """[gate 0..63 | up 0..63 | gate 64..127 | up 64..127 | ...]: each 128-row MMA tile carries the
+    gate and up rows of the same 64 output features (csrc/gemm_tc.cu EPI_GLU)."""
+    f, h = w_gate.shape
+    assert f % 64 == 0
+    g = w_gate.view(f // 64, 64, h)
+    u = w_up.view(f // 64, 64, h)
+    return torch.cat([g, u], 1).reshape(2 * f, h).contiguous()
+
+
+def fold_gamma(w: torch.Tensor, gamma: torch.Tensor, plus_one: bool = False) -> torch.Tensor:
+    """W' = W diag(gamma): RMSNorm's scale folded into the consuming projection."""
+    g = gamma.float() + 1.0 if plus_one else gamma.float()
+    return (w.float() * g[None, :]).to(w.dtype).contiguous()
+
+
+def pad_rows(w: torch.Tensor, multiple: int = 128) -> torch.Tensor:
+    r = w.shape[0]
+    pad = (-r) % multiple
+    if pad == 0:
+        return w.contiguous()
+    return torch.cat([w, w.new_zeros((pad, *w.shape[1:]))], 0).contiguous()
+
+
+# ------------------------------------------------------------------------ GEMM
+def pick_bn(m_tok: int) -> int:
+    for bn in (16, 32, 64, 128):
+        if m_tok <= bn:
+            return bn
+    return 256 if m_tok > 512 else 128
+
+
+def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
+    tiles = (n_out // 128) * ((m_tok + bn - 1) // bn)
+    if tiles >= NUM_SMS:
+        return 1
+    want = max(1, round(2 * NUM_SMS / tiles) if tiles * 2 <= NUM_SMS else 1)
+    want = min(want, 8, max(1, (k // 64) // 4))
+    return max(1, min(want, native().gemm_max_splitk(bn, epi)))
+
+
+def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, epi: int = EPI_PLAIN,
+         residual: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         rstd: Optional[torch.Tensor] = None, norm_from_x: bool = False, eps: float = 1e-5, act_gelu: bool = False,
+         out_fp32: bool = False, bn: int = 0, splitk: int = 0,
+         q_out=None, k_cache=None, v_cache=None, positions=None, slots=None, n_q_heads: int = 0,
+         n_kv_heads: int = 0, head_dim: int = 0, rope_theta: float = 0.0, q_scale: float = 1.0,
+         out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
+         wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
+         done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0) -> Optional[torch.Tensor]:
+    """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
+    m_tok, k = x.shape
+    n_out = w.shape[0]
+    if bn <= 0:
+        bn = pick_bn(m_tok)
+    if splitk <= 0:
+        splitk = pick_splitk(n_out, m_tok, k, bn, epi)
+    if epi == EPI_QKV_ROPE:
+        o_ptr, ldo = 0, 0
+    elif out_ptr:
+        o_ptr, ldo = out_ptr, ld_out
+    else:
+        if out is None:
+            width = n_out // 2 if epi == EPI_GLU else n_out
+            out = torch.empty((m_tok, width), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        o_ptr, ldo = out.data_ptr(), out.stride(0)
+    if residual is not None:
+        residual_ptr, ld_res = residual.data_ptr(), residual.stride(0)
+    native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
+                  out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
+                  q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
+                  ack_flag)
+    return out
+
+
+# ----------------------------------------------------------------- elementwise
+def rmsnorm(x, gamma, out=None, residual=None, eps=1e-5, plus_one=False, rstd_out=None, want_out=True):
+    if out is None and want_out:
+        out = torch.empty_like(x)
+    native().rmsnorm(x, gamma, residual, out, rstd_out, eps, plus_one)
+    return out
+
+
+def rstd(x, eps=1e-5):
+    """per-token 1/rms (fp32) for GEMMs whose RMSNorm is fused but whose token tile is large"""
+    r = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    native().rmsnorm(x, x, None, None, r, eps, False)
+    return r
+
+
+def layernorm(x, gamma, beta, out=None, eps=1e-5):
+    if out is None:
+        out = torch.empty_like(x)
+    native().layernorm(x, gamma, beta, out, eps)
+    return out
+
+
+def embed(ids, table, out, pos_table=None, positions=None, scale=1.0, tok_flag=0, tok_epoch=0):
+    native().embed(ids.data_ptr() if isinstance(ids, torch.Tensor) else int(ids), table, pos_table, positions, out,
+                   scale, tok_flag, tok_epoch)
+    return out
+
+
+def kv_append(qkv, q_out, k_cache, v_cache, slots, q_dim, kv_dim, q_scale):
+    native().kv_append(qkv, q_out, k_cache, v_cache, slots, q_dim, kv_dim, q_scale)
+
+
+def add(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    native().add(a, b, out)
+    return out
+
+
+# -------------------------------------------------------------------- attention
+def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, max_q, n_q, n_kv, head_dim,
+              window=0, softcap=0.0, splits=1, ws=None):
+    native().attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, ws, max_q, n_q, n_kv, head_dim,
+                       window, softcap, splits)
+    return out
+
+
+# ---------------------------------------------------------------------- sampler
+def sample(logits, out_tokens, *, seen=None, temperature=None, top_p=None, rep_penalty=None, seeds=None, step=None,
+           peer_tokens=0, history=0, hist_pos=None, hist_stride=0, signal_flag=0, signal_epoch=0, done_counter=0,
+           vocab=0, softcap=0.0):
+    native().sample(logits, seen, out_tokens, peer_tokens, history, hist_pos, hist_stride, vocab, softcap,
+                    temperature, top_p,
+                    rep_penalty, seeds, step, signal_flag, signal_epoch, done_counter)
+    return out_tokens
+
+
+def mark_seen(ids, seq_of, seen, vocab):
+    native().mark_seen(ids, seq_of, seen, vocab)

@@ -1,0 +1,172 @@
+"""NVLink mesh: the in-process replacement for the reference's WAN discovery and transport.
+
+``peer = one B200 hosting one piece``.  What the reference does with bootstrap links,
+hello/peer_list gossip, DHT lookups, STUN/UPnP and one WebSocket per peer pair
+(/root/reference/bee2bee/p2p_runtime.py:308-372,478-523; dht.py; nat.py) collapses into
+
+  * a topology table  rank <-> cuda device <-> piece (layer range), canAccessPeer matrix,
+  * symmetric staging buffers + flags whose CUDA IPC handles are exchanged ONCE through
+    ``torch.distributed`` (one process per GPU) -- afterwards the token path is pure
+    device-to-device: kernels store into peer-mapped memory and publish release flags,
+  * ``cudaMemcpyPeerAsync`` for bulk moves (weights, KV migration).
+
+``MeshComm`` also works for world_size == 1 (no peers, no flags).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+from ..models.native import Handoff
+
+FLAG_WORDS = 16          # u32 slots per group (64 B, one line per group)
+F_IN_FLAG, F_IN_EPOCH, F_OUT_EPOCH, F_OUT_FREE, F_DONE, F_TOK_DONE = 0, 1, 2, 3, 4, 5
+
+
+@dataclass
+class PeerInfo:
+    rank: int
+    device: int
+    pid: int
+    host: str
+    layers: List[int] = field(default_factory=list)
+
+
+class MeshComm:
+    """Per-rank view of the pipeline ring rank0 -> rank1 -> ... -> rank(W-1) -> rank0 (tokens)."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, hidden: int, max_tokens: int, groups: int,
+                 group_batch: int, hist_len: int, control_group=None):
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.hidden, self.max_tokens, self.groups, self.group_batch, self.hist_len = hidden, max_tokens, groups, group_batch, hist_len
+        self.control_group = control_group
+        self.next_rank = (rank + 1) % world
+        self.prev_rank = (rank - 1) % world
+        self.peers: Dict[int, PeerInfo] = {}
+        self._opened: List[int] = []
+        self.C = ops.native() if self.device.type == "cuda" else None
+        self.local: Dict[str, int] = {}
+        self.remote_next: Dict[str, int] = {}
+        self.remote_prev: Dict[str, int] = {}
+        self.remote_first: Dict[str, int] = {}
+        if world > 1:
+            self._alloc_and_exchange()
+
+    # ------------------------------------------------------------------ set-up
+    def _sizes(self) -> Dict[str, int]:
+        return {
+            "stage": self.groups * self.max_tokens * self.hidden * 2,           # bf16 staging per group
+            "flags": self.groups * FLAG_WORDS * 4,
+            "tok": self.groups * self.group_batch * 4,                          # sampled-token return buffer (rank 0)
+            "hist": self.groups * self.group_batch * self.hist_len * 4,         # token history ring (rank 0)
+        }
+
+    def _alloc_and_exchange(self) -> None:
+        import torch.distributed as dist
+
+        C = self.C
+        handles = {}
+        for name, nbytes in self._sizes().items():
+            p = C.peer_alloc(max(256, nbytes))
+            self.local[name] = p
+            handles[name] = C.ipc_export(p)
+        info = {"rank": self.rank, "device": self.device.index, "pid": os.getpid(), "host": os.uname().nodename,
+                "handles": handles}
+        gathered: List[Optional[dict]] = [None] * self.world
+        dist.all_gather_object(gathered, info, group=self.control_group)
+        for g in gathered:
+            self.peers[g["rank"]] = PeerInfo(g["rank"], g["device"], g["pid"], g["host"])
+
+        def open_all(rank: int) -> Dict[str, int]:
+            if rank == self.rank:
+                return dict(self.local)
+            out = {}
+            for name, h in gathered[rank]["handles"].items():
+                p = C.ipc_import(h)
+                self._opened.append(p)
+                out[name] = p
+            return out
+
+        self.remote_next = open_all(self.next_rank)
+        self.remote_prev = open_all(self.prev_rank) if self.prev_rank != self.next_rank else self.remote_next
+        self.remote_first = self.remote_next if self.next_rank == 0 else (
+            self.remote_prev if self.prev_rank == 0 else open_all(0))
+        dist.barrier(group=self.control_group)
+
+    # ------------------------------------------------------------------ endpoints
+    def _flag(self, table: Dict[str, int], group: int, word: int) -> int:
+        return table["flags"] + (group * FLAG_WORDS + word) * 4
+
+    def handoff(self, group: int) -> Handoff:
+        """Addresses for micro-batch group ``group`` on this rank (all zero for world == 1)."""
+        if self.world == 1:
+            return Handoff()
+        first, last = self.rank == 0, self.rank == self.world - 1
+        stage_off = group * self.max_tokens * self.hidden * 2
+        tok_off = group * self.group_batch * 4
+        h = Handoff()
+        h.in_flag = self._flag(self.local, group, F_IN_FLAG)
+        h.in_epoch = self._flag(self.local, group, F_IN_EPOCH)
+        h.out_epoch = self._flag(self.local, group, F_OUT_EPOCH)
+        h.out_free = 0                                   # decode: implied by the token loop
+        h.done = self._flag(self.local, group, F_DONE)
+        h.in_x = (self.local["tok"] + tok_off) if first else (self.local["stage"] + stage_off)
+        h.up_ack = 0
+        if last:
+            h.out_x = self.remote_first["tok"] + tok_off
+            h.out_flag = self._flag(self.remote_first, group, F_IN_FLAG)
+        else:
+            h.out_x = self.remote_next["stage"] + stage_off
+            h.out_flag = self._flag(self.remote_next, group, F_IN_FLAG)
+        return h
+
+    def history_ptr(self, group: int) -> int:
+        """Where the sampler of the last rank writes token history (rank 0's ring)."""
+        table = self.remote_first if self.world > 1 else self.local
+        return table["hist"] + group * self.group_batch * self.hist_len * 4
+
+    def local_view(self, name: str, shape, dtype: str) -> torch.Tensor:
+        return self.C.tensor_from_ptr(self.local[name], list(shape), dtype, self.device.index)
+
+    def reset_flags(self, token_ready: bool = True) -> None:
+        """Between bursts (GPU idle, host barrier on both sides): zero all local flags; on rank 0
+        mark the token buffer as already produced once (it was filled by prefill / last burst)."""
+        if self.world == 1:
+            return
+        flags = self.local_view("flags", (self.groups, FLAG_WORDS), "i32")
+        flags.zero_()
+        if self.rank == 0 and token_ready:
+            flags[:, F_IN_FLAG] = 1
+        if self.rank == self.world - 1 and token_ready:
+            flags[:, F_OUT_EPOCH] = 1
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.control_group)
+
+    def topology(self) -> Dict:
+        n = torch.cuda.device_count() if self.device.type == "cuda" else 0
+        acc = [[bool(i == j or (self.C and self.C.can_access_peer(i, j))) for j in range(n)] for i in range(n)]
+        return {"rank": self.rank, "world": self.world, "device": str(self.device), "can_access_peer": acc,
+                "peers": {r: vars(p) for r, p in self.peers.items()}}
+
+    def close(self) -> None:
+        if self.C is None:
+            return
+        for p in self._opened:
+            try:
+                self.C.ipc_close(p)
+            except Exception:
+                pass
+        self._opened.clear()
+        for p in self.local.values():
+            try:
+                self.C.peer_free(p)
+            except Exception:
+                pass
+        self.local.clear()

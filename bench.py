@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): decode tokens/s + p50 TTFT for Llama-3-8B (bf16,
+random-init weights, synthetic 16-token prompts) split into N pieces on N B200s.
+
+    python bench.py --gpus 1 --steps 64 --warmup 8
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # unmodified reference (baseline/_ref), HFService path
+
+ours: every GPU hosts one contiguous layer range ("piece"); N micro-batch groups of
+`--batch` sequences travel through the pieces as a wavefront; the hop between pieces is the
+fused tail-GEMM -> NVLink peer store -> flag -> head-GEMM path, no NCCL on the token path.
+One "step" = one decode step of every group = N * batch new tokens (weak scaling: per-GPU
+token work is fixed, the model is sliced thinner).  Timing: CUDA events on the launch
+stream, barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--batch", type=int, default=32, help="sequences per micro-batch group")
+    ap.add_argument("--groups", type=int, default=0, help="micro-batch groups in flight (default: N)")
+    ap.add_argument("--prompt-len", type=int, default=16)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def baseline_number():
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            pub = json.load(f).get("published") or {}
+        for v in pub.values():
+            if isinstance(v, (int, float)):
+                return float(v)
+    except Exception:
+        pass
+    return None
+
+
+def synthetic_prompts(n, length, vocab):
+    return [[(7 + 131 * i + 31 * j) % (vocab - 300) + 256 for j in range(length)] for i in range(n)]
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+
+    from bee2bee_b200.engine.core import Engine, SamplingParams
+    from bee2bee_b200.engine.runner import GpuRunner, SeqInit
+    from bee2bee_b200.models.config import resolve_config
+    from bee2bee_b200.parallel.dist import init_distributed, max_over_ranks, shutdown
+
+    rank, world, local = init_distributed()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    cfg = resolve_config(args.model)
+    groups = args.groups or world
+    B = args.batch
+    total = B * groups
+    K, W = args.steps, max(3, args.warmup)
+    P = args.prompt_len
+    max_seq = 1024 if (P + 2 * (K + W) + 64) <= 1024 else P + 2 * (K + W) + 64
+    eng = Engine(args.model, cfg=cfg, device=str(dev), max_batch=total, groups=groups, max_seq_len=max_seq,
+                 max_prefill_tokens=max(512, P * min(total, 32)), decode_burst=K, rank=rank, world=world)
+    runner: GpuRunner = eng.runner
+    prompts = synthetic_prompts(total, P, cfg.vocab_size)
+
+    def barrier_sync():
+        torch.cuda.synchronize(dev)
+        runner.mesh.barrier()
+
+    # ---------------- kernel-path measurement: prefill once, then W + K device-side decode steps
+    need = P + W + K + 8
+    seqs = [SeqInit(slot=i, prompt=prompts[i], pages=list(range(1 + i * ((need + 63) // 64), 1 + (i + 1) * ((need + 63) // 64))),
+                    temperature=0.7, top_p=0.95, repetition_penalty=1.15, seed=1000 + i) for i in range(total)]
+    # p50 TTFT: single 16-token request, prefill -> first token, device-timed
+    ttfts = []
+    for rep in range(5):
+        barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(runner.stream)
+        runner.prefill(seqs[:1])
+        e1.record(runner.stream)
+        barrier_sync()
+        ttfts.append(max_over_ranks(e0.elapsed_time(e1), dev))
+        runner.release([0])
+    runner.prefill(seqs)
+    runner.decode(W)
+    barrier_sync()
+    launches0 = runner.kernel_launches
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    flush.fill_(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    runner.prepare_burst()
+    barrier_sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(runner.stream)
+    runner.decode(K, prepared=True)
+    e1.record(runner.stream)
+    barrier_sync()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = runner.kernel_launches - launches0
+    hist, _ = runner.read_history() if rank == 0 else (None, None)
+    if rank == 0:
+        got = hist[:total, : 1 + W + K]
+        assert int((got >= 0).all()) and int((got < cfg.vocab_size).all()), "sampler produced out-of-range ids"
+        uniq = len(set(got[:, -1].tolist()))
+    runner.release(list(range(total)))
+    tok_s = total * K / (ms / 1e3)
+
+    # ---------------- end-to-end through the public API (Engine.generate): host prompts in pinned
+    # memory -> H2D, scheduler, prefill + decode bursts, D2H token reads every burst.
+    e2e = None
+    if not args.no_e2e:
+        sp = SamplingParams(max_new_tokens=K, temperature=0.7, top_p=0.95, repetition_penalty=1.15, ignore_eos=True,
+                            seed=7)
+        eng.decode_burst = 16
+        eng.generate(prompts[: min(total, 4)], SamplingParams(max_new_tokens=4, ignore_eos=True))   # warm
+        eng.h2d_bytes = eng.d2h_bytes = 0
+        h0 = runner.h2d_bytes
+        barrier_sync()
+        t0 = time.perf_counter()
+        outs = eng.generate(prompts, sp)
+        barrier_sync()
+        dt = max_over_ranks(time.perf_counter() - t0, dev)
+        n_tok = sum(len(o) for o in outs)
+        e2e = {"value": n_tok / dt, "unit": "tokens/s", "wall_s": dt,
+               "h2d_bytes_per_step": (eng.h2d_bytes + runner.h2d_bytes - h0) / K,
+               "d2h_bytes_per_step": eng.d2h_bytes / K, "includes": "prefill+decode, scheduler, token readback"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        wbytes = runner.piece.weight_bytes()
+        step_ms = ms / K
+        # every group step streams this rank's weights once
+        hbm = wbytes * groups / (step_ms / 1e3) / 1e9
+        base = baseline_number()
+        out = {"metric": "decode_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
+               "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": (tok_s / base) if base else None, "dtype": "bf16", "data": "synthetic",
+               "impl": "ours",
+               "config": {"model": args.model, "global_batch": total, "seq_len": P + W + K, "prompt_len": P,
+                          "parallelism": f"pp{world}", "pieces": world, "micro_batch_groups": groups,
+                          "batch_per_group": B, "weights": "random-init", "sampling": "T=0.7 top_p=0.95 rep=1.15",
+                          "l2": "per-step weight stream (>=2 GB/GPU) exceeds the 126 MB L2; L2 flushed before timing"},
+               "p50_ttft_ms": statistics.median(ttfts), "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+               "roofline": {"weight_bytes_per_gpu": wbytes, "achieved_weight_stream_GBps": hbm,
+                            "hbm_frac_of_measured": (hbm / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None},
+               "distinct_last_tokens": uniq}
+        print(json.dumps(out), flush=True)
+    eng.close()
+    shutdown()
+
+
+# ------------------------------------------------------------------------- reference
+def run_reference(args):
+    """Unmodified reference (baseline/_ref): HFService -> transformers.generate on one GPU per rank
+    (the reference has no multi-GPU path; N ranks = N independent replica providers, which is its own
+    "load balancing" story, /root/reference/bee2bee/p2p_runtime.py:723-757)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "bee2bee")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed"}))
+        return
+    sys.path.insert(0, ref)
+    try:
+        import torch
+        from bee2bee.services import HFService  # noqa
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"import failed: {e!r}"[:200]}))
+        return
+    from baseline.ref_model import build_reference_checkpoint   # builds config/tokenizer/weights with transformers
+    from bee2bee_b200.parallel.dist import init_distributed, max_over_ranks, shutdown
+
+    rank, world, local = init_distributed()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    K, W, B, P = args.steps, max(3, args.warmup), args.batch, args.prompt_len
+    total = B * (args.groups or world)
+    per_rank = total // world
+    path = build_reference_checkpoint(args.model, rank)
+    svc = HFService(path, 0.0)
+    svc.load_sync()
+    prompts = [" ".join(f"t{(7 + 131 * i + 31 * j) % 100000 + 300}" for j in range(P)) for i in range(total)]
+    mine = prompts[rank * per_rank:(rank + 1) * per_rank]
+    svc.execute({"prompt": mine[0], "max_new_tokens": W, "temperature": 0.7})
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    toks = 0
+    for p in mine:
+        r = svc.execute({"prompt": p, "max_new_tokens": K, "temperature": 0.7})
+        toks += int(r.get("tokens") or K)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, "cuda" if torch.cuda.is_available() else None)
+    clocks = sampler.stop() if rank == 0 else {}
+    if rank == 0:
+        val = toks * world / dt
+        print(json.dumps({"metric": "decode_tokens_per_sec", "value": val, "unit": "tokens/s", "n_gpus": world,
+                          "steps": K, "warmup": W, "ms_per_step": dt * 1e3 / K, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "impl": "reference",
+                          "config": {"model": args.model, "global_batch": total, "seq_len": P + K, "prompt_len": P,
+                                     "parallelism": f"replica x{world} (reference has no model parallelism)",
+                                     "path": "HFService.execute -> transformers.generate, one request at a time"},
+                          "clocks": clocks, "e2e": {"value": val, "unit": "tokens/s"}, "gpu_launches": 0}), flush=True)
+    shutdown()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

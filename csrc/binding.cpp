@@ -1,0 +1,312 @@
+// Python bindings (torch extension `bee2bee_b200._C`).  The only torch-facing translation
+// unit: it validates tensors, picks the current CUDA stream and calls the C launchers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gemm_tc.cuh"
+#include "kernels.h"
+#include "peer.h"
+
+using at::Tensor;
+using OptT = c10::optional<Tensor>;
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check(int err, const char* what) {
+  if (err != 0) {
+    const char* msg = err > 0 ? cudaGetErrorString(static_cast<cudaError_t>(err)) : "invalid argument";
+    TORCH_CHECK(false, what, " failed: code ", err, " (", msg, ")");
+  }
+}
+template <typename T>
+inline T* ptr_or_null(const OptT& t) {
+  return (t.has_value() && t->defined()) ? reinterpret_cast<T*>(t->data_ptr()) : nullptr;
+}
+template <typename T>
+inline T* as_ptr(int64_t addr) { return reinterpret_cast<T*>(static_cast<uintptr_t>(addr)); }
+
+void check_bf16(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous(), name,
+              " must be a contiguous CUDA bf16 tensor");
+}
+
+// ---------------------------------------------------------------------- GEMM
+// out[t, n] = epi(X[t,:] . W[n,:]).  Handoff pointers are raw device addresses (0 = unused)
+// because they may live in IPC-mapped peer memory.
+void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int64_t epi, int64_t bn,
+          int64_t splitk, int64_t residual_ptr, int64_t ld_res, const OptT& bias, const OptT& rstd,
+          bool norm_from_x, double eps, bool act_gelu, bool out_fp32,
+          // qkv epilogue
+          const OptT& q_out, const OptT& k_cache, const OptT& v_cache, const OptT& positions, const OptT& slots,
+          int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, double rope_theta, double q_scale,
+          // handoff
+          int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
+          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag) {
+  check_bf16(w, "w");
+  check_bf16(x, "x");
+  TORCH_CHECK(w.dim() == 2 && x.dim() == 2 && w.size(1) == x.size(1), "gemm: shape mismatch");
+  c10::cuda::CUDAGuard guard(w.device());
+  b2b::GemmParams p{};
+  p.m_tok = static_cast<int>(x.size(0));
+  p.n_out = static_cast<int>(w.size(0));
+  p.k = static_cast<int>(w.size(1));
+  p.splitk = static_cast<int>(splitk);
+  p.epi = static_cast<int>(epi);
+  p.out_fp32 = out_fp32 ? 1 : 0;
+  p.act_gelu = act_gelu ? 1 : 0;
+  p.out = as_ptr<void>(out_ptr);
+  p.ld_out = static_cast<int>(ld_out);
+  p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
+  p.ld_res = static_cast<int>(ld_res);
+  p.bias = ptr_or_null<const float>(bias);
+  p.rstd = ptr_or_null<const float>(rstd);
+  p.norm_src = norm_from_x ? reinterpret_cast<const __nv_bfloat16*>(x.data_ptr()) : nullptr;
+  p.eps = static_cast<float>(eps);
+  p.q_out = ptr_or_null<__nv_bfloat16>(q_out);
+  p.k_cache = ptr_or_null<__nv_bfloat16>(k_cache);
+  p.v_cache = ptr_or_null<__nv_bfloat16>(v_cache);
+  p.positions = ptr_or_null<const int>(positions);
+  p.slots = ptr_or_null<const int>(slots);
+  p.n_q_heads = static_cast<int>(n_q_heads);
+  p.n_kv_heads = static_cast<int>(n_kv_heads);
+  p.head_dim = static_cast<int>(head_dim);
+  p.rope_theta = static_cast<float>(rope_theta);
+  p.q_scale = static_cast<float>(q_scale);
+  p.wait_flag = as_ptr<const uint32_t>(wait_flag);
+  p.wait_epoch = as_ptr<const uint32_t>(wait_epoch);
+  p.signal_flag = as_ptr<uint32_t>(signal_flag);
+  p.signal_epoch = as_ptr<uint32_t>(signal_epoch);
+  p.done_counter = as_ptr<uint32_t>(done_counter);
+  p.free_flag = as_ptr<const uint32_t>(free_flag);
+  p.bump_epoch = as_ptr<uint32_t>(bump_epoch);
+  p.ack_flag = as_ptr<uint32_t>(ack_flag);
+  if (p.epi == b2b::EPI_QKV_ROPE) {
+    TORCH_CHECK(p.q_out && p.k_cache && p.v_cache && p.slots, "qkv epilogue needs q_out/k_cache/v_cache/slots");
+    TORCH_CHECK(p.rope_theta <= 0.f || p.positions, "rope needs positions");
+    TORCH_CHECK((p.n_q_heads * p.head_dim) % 128 == 0 && (p.n_kv_heads * p.head_dim) % 128 == 0,
+                "q/kv widths must be multiples of 128");
+    TORCH_CHECK(p.n_out == (p.n_q_heads + 2 * p.n_kv_heads) * p.head_dim, "qkv rows mismatch");
+  }
+  if (p.epi == b2b::EPI_RESIDUAL) TORCH_CHECK(p.residual != nullptr, "residual epilogue needs residual");
+  if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
+  check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
+}
+
+int64_t gemm_max_splitk(int64_t bn, int64_t epi) {
+  return b2b::gemm_tc_max_splitk(static_cast<int>(bn), static_cast<int>(epi));
+}
+
+void init_kernels(int64_t device) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  check(b2b::gemm_tc_init(), "gemm_tc_init");
+  check(b2b::attention_init(), "attention_init");
+}
+
+// ----------------------------------------------------------------- elementwise
+void rmsnorm(const Tensor& x, const Tensor& gamma, const OptT& residual, const OptT& out, const OptT& rstd_out,
+             double eps, bool gemma_plus_one) {
+  check_bf16(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = static_cast<int>(x.size(-1));
+  const int tokens = static_cast<int>(x.numel() / h);
+  check(b2b::launch_rmsnorm(x.data_ptr(), gamma.data_ptr(), ptr_or_null<void>(residual), ptr_or_null<void>(out),
+                            ptr_or_null<float>(rstd_out), tokens, h, static_cast<float>(eps), gemma_plus_one ? 1 : 0,
+                            cur_stream()),
+        "rmsnorm");
+}
+
+void layernorm(const Tensor& x, const Tensor& gamma, const Tensor& beta, const Tensor& out, double eps) {
+  check_bf16(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = static_cast<int>(x.size(-1));
+  check(b2b::launch_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                              static_cast<int>(x.numel() / h), h, static_cast<float>(eps), cur_stream()),
+        "layernorm");
+}
+
+void embed(int64_t ids_ptr, const Tensor& table, const OptT& pos_table, const OptT& positions, const Tensor& out,
+           double scale, int64_t tok_flag, int64_t tok_epoch) {
+  check_bf16(table, "table");
+  c10::cuda::CUDAGuard guard(table.device());
+  const int h = static_cast<int>(table.size(1));
+  check(b2b::launch_embed(as_ptr<const int>(ids_ptr), table.data_ptr(), ptr_or_null<void>(pos_table),
+                          ptr_or_null<const int>(positions), out.data_ptr(), static_cast<int>(out.numel() / h), h,
+                          static_cast<int>(table.size(0)), static_cast<float>(scale), as_ptr<const uint32_t>(tok_flag),
+                          as_ptr<const uint32_t>(tok_epoch), cur_stream()),
+        "embed");
+}
+
+void kv_append(const Tensor& qkv, const Tensor& q_out, const Tensor& k_cache, const Tensor& v_cache,
+               const Tensor& slots, int64_t q_dim, int64_t kv_dim, double q_scale) {
+  check_bf16(qkv, "qkv");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  check(b2b::launch_kv_append(qkv.data_ptr(), q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                              reinterpret_cast<const int*>(slots.data_ptr()), static_cast<int>(qkv.size(0)),
+                              static_cast<int>(q_dim), static_cast<int>(kv_dim), static_cast<float>(q_scale),
+                              cur_stream()),
+        "kv_append");
+}
+
+void add(const Tensor& a, const Tensor& b, const Tensor& out) {
+  check_bf16(a, "a");
+  c10::cuda::CUDAGuard guard(a.device());
+  check(b2b::launch_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), static_cast<size_t>(a.numel()), cur_stream()),
+        "add");
+}
+
+void flag_wait(int64_t flag, int64_t epoch, int64_t delta) {
+  check(b2b::launch_flag_wait(as_ptr<const uint32_t>(flag), as_ptr<const uint32_t>(epoch),
+                              static_cast<uint32_t>(delta), cur_stream()),
+        "flag_wait");
+}
+void decode_advance(const Tensor& positions, const Tensor& kv_len, const Tensor& slots, const Tensor& q_len,
+                    const Tensor& block_table) {
+  c10::cuda::CUDAGuard guard(positions.device());
+  check(b2b::launch_decode_advance(reinterpret_cast<int*>(positions.data_ptr()), reinterpret_cast<int*>(kv_len.data_ptr()),
+                                   reinterpret_cast<int*>(slots.data_ptr()),
+                                   reinterpret_cast<const int*>(q_len.data_ptr()),
+                                   reinterpret_cast<const int*>(block_table.data_ptr()),
+                                   static_cast<int>(block_table.size(1)), static_cast<int>(positions.numel()),
+                                   cur_stream()),
+        "decode_advance");
+}
+void flag_signal(int64_t flag, int64_t epoch, int64_t bump_epoch, int64_t ack_flag) {
+  check(b2b::launch_flag_signal(as_ptr<uint32_t>(flag), as_ptr<uint32_t>(epoch), as_ptr<uint32_t>(bump_epoch),
+                                as_ptr<uint32_t>(ack_flag), cur_stream()),
+        "flag_signal");
+}
+
+// -------------------------------------------------------------------- attention
+void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& out,
+               const Tensor& block_table, const Tensor& q_start, const Tensor& q_len, const Tensor& kv_len,
+               const OptT& ws, int64_t max_q, int64_t n_q, int64_t n_kv, int64_t head_dim, int64_t window,
+               double softcap, int64_t splits) {
+  check_bf16(q, "q");
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && q_len.scalar_type() == at::kInt, "int32 metadata expected");
+  const int seqs = static_cast<int>(q_len.size(0));
+  if (splits > 1) {
+    TORCH_CHECK(ws.has_value(), "split-KV needs a workspace");
+    const int64_t R = b2b::attn_rows(static_cast<int>(n_q / n_kv), 1);
+    TORCH_CHECK(ws->numel() >= seqs * n_kv * splits * R * (head_dim + 2), "attention workspace too small");
+  }
+  check(b2b::launch_attention(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+                              reinterpret_cast<const int*>(block_table.data_ptr()),
+                              reinterpret_cast<const int*>(q_start.data_ptr()),
+                              reinterpret_cast<const int*>(q_len.data_ptr()),
+                              reinterpret_cast<const int*>(kv_len.data_ptr()), ptr_or_null<float>(ws), seqs,
+                              static_cast<int>(max_q), static_cast<int>(block_table.size(1)), static_cast<int>(n_q),
+                              static_cast<int>(n_kv), static_cast<int>(head_dim), static_cast<int>(window),
+                              static_cast<float>(softcap), static_cast<int>(splits), cur_stream()),
+        "attention");
+}
+
+// ---------------------------------------------------------------------- sampler
+void sample(const Tensor& logits, const OptT& seen, const Tensor& out_tokens, int64_t peer_tokens,
+            int64_t history, const OptT& hist_pos, int64_t hist_stride, int64_t vocab, double softcap,
+            const OptT& temperature, const OptT& top_p,
+            const OptT& rep_penalty, const OptT& seeds, const OptT& step, int64_t signal_flag, int64_t signal_epoch,
+            int64_t done_counter) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.stride(1) == 1, "logits: fp32");
+  c10::cuda::CUDAGuard guard(logits.device());
+  int* hp = ptr_or_null<int>(hist_pos);
+  check(b2b::launch_sample(reinterpret_cast<const float*>(logits.data_ptr()), ptr_or_null<uint32_t>(seen),
+                           reinterpret_cast<int*>(out_tokens.data_ptr()), as_ptr<int>(peer_tokens),
+                           as_ptr<int>(history), hp, hp, static_cast<int>(hist_stride),
+                           static_cast<int>(logits.size(0)), static_cast<int>(vocab > 0 ? vocab : logits.size(1)),
+                           static_cast<int>(logits.stride(0)), static_cast<float>(softcap),
+                           ptr_or_null<const float>(temperature), ptr_or_null<const float>(top_p),
+                           ptr_or_null<const float>(rep_penalty), ptr_or_null<const uint32_t>(seeds),
+                           ptr_or_null<const uint32_t>(step), as_ptr<uint32_t>(signal_flag),
+                           as_ptr<uint32_t>(signal_epoch), as_ptr<uint32_t>(done_counter), cur_stream()),
+        "sample");
+}
+
+void mark_seen(const Tensor& ids, const Tensor& seq_of, const Tensor& seen, int64_t vocab) {
+  c10::cuda::CUDAGuard guard(ids.device());
+  check(b2b::launch_mark_seen(reinterpret_cast<const int*>(ids.data_ptr()),
+                              reinterpret_cast<const int*>(seq_of.data_ptr()),
+                              reinterpret_cast<uint32_t*>(seen.data_ptr()), static_cast<int>(ids.numel()),
+                              static_cast<int>(vocab), cur_stream()),
+        "mark_seen");
+}
+
+// ------------------------------------------------------------------ peer memory
+int64_t peer_alloc(int64_t bytes) {
+  void* p = nullptr;
+  check(b2b::peer_alloc(static_cast<size_t>(bytes), &p), "peer_alloc");
+  return static_cast<int64_t>(reinterpret_cast<uintptr_t>(p));
+}
+void peer_free(int64_t p) { check(b2b::peer_free(as_ptr<void>(p)), "peer_free"); }
+py::bytes ipc_export(int64_t p) {
+  char h[64];
+  check(b2b::ipc_export(as_ptr<void>(p), h), "cudaIpcGetMemHandle");
+  return py::bytes(h, 64);
+}
+int64_t ipc_import(const std::string& handle) {
+  TORCH_CHECK(handle.size() == 64, "IPC handle must be 64 bytes");
+  void* p = nullptr;
+  check(b2b::ipc_import(handle.data(), &p), "cudaIpcOpenMemHandle");
+  return static_cast<int64_t>(reinterpret_cast<uintptr_t>(p));
+}
+void ipc_close(int64_t p) { check(b2b::ipc_close(as_ptr<void>(p)), "cudaIpcCloseMemHandle"); }
+void enable_peer_access(int64_t dev, int64_t peer) {
+  check(b2b::enable_peer_access(static_cast<int>(dev), static_cast<int>(peer)), "cudaDeviceEnablePeerAccess");
+}
+bool can_access_peer(int64_t dev, int64_t peer) {
+  return b2b::can_access_peer(static_cast<int>(dev), static_cast<int>(peer)) != 0;
+}
+void memcpy_peer(int64_t dst, int64_t dst_dev, int64_t src, int64_t src_dev, int64_t bytes) {
+  check(b2b::memcpy_peer_async(as_ptr<void>(dst), static_cast<int>(dst_dev), as_ptr<const void>(src),
+                               static_cast<int>(src_dev), static_cast<size_t>(bytes), cur_stream()),
+        "cudaMemcpyPeerAsync");
+}
+std::pair<int64_t, int64_t> host_ring_alloc(int64_t bytes) {
+  void *h = nullptr, *d = nullptr;
+  check(b2b::host_ring_alloc(static_cast<size_t>(bytes), &h, &d), "cudaHostAlloc");
+  return {static_cast<int64_t>(reinterpret_cast<uintptr_t>(h)), static_cast<int64_t>(reinterpret_cast<uintptr_t>(d))};
+}
+void host_ring_free(int64_t h) { check(b2b::host_ring_free(as_ptr<void>(h)), "cudaFreeHost"); }
+
+// View raw (possibly peer-mapped or host-mapped) memory as a tensor; no ownership.
+Tensor tensor_from_ptr(int64_t p, std::vector<int64_t> sizes, const std::string& dtype, int64_t device) {
+  at::ScalarType st = dtype == "bf16" ? at::kBFloat16 : dtype == "f32" ? at::kFloat : dtype == "i32" ? at::kInt
+                      : dtype == "u8" ? at::kByte : at::kLong;
+  auto opts = at::TensorOptions().dtype(st);
+  opts = device >= 0 ? opts.device(at::kCUDA, static_cast<c10::DeviceIndex>(device)) : opts.device(at::kCPU);
+  return at::from_blob(as_ptr<void>(p), sizes, opts);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "bee2bee_b200 native sm_100a kernels + NVLink peer-memory runtime";
+  m.def("gemm", &gemm);
+  m.def("gemm_max_splitk", &gemm_max_splitk);
+  m.def("init_kernels", &init_kernels);
+  m.def("rmsnorm", &rmsnorm);
+  m.def("layernorm", &layernorm);
+  m.def("embed", &embed);
+  m.def("kv_append", &kv_append);
+  m.def("add", &add);
+  m.def("flag_wait", &flag_wait);
+  m.def("flag_signal", &flag_signal);
+  m.def("decode_advance", &decode_advance);
+  m.def("attention", &attention);
+  m.def("sample", &sample);
+  m.def("mark_seen", &mark_seen);
+  m.def("peer_alloc", &peer_alloc);
+  m.def("peer_free", &peer_free);
+  m.def("ipc_export", &ipc_export);
+  m.def("ipc_import", &ipc_import);
+  m.def("ipc_close", &ipc_close);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("can_access_peer", &can_access_peer);
+  m.def("memcpy_peer", &memcpy_peer);
+  m.def("host_ring_alloc", &host_ring_alloc);
+  m.def("host_ring_free", &host_ring_free);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+}

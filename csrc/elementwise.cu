@@ -1,0 +1,246 @@
+// Bandwidth-bound helper kernels for sm_100a: RMSNorm / LayerNorm, embedding gather
+// (optionally gated on the sampled-token flag written by the last piece over NVLink),
+// KV append for the unfused path, per-token 1/rms.  All 128-bit vectorised.
+// Reference parity: the ATen elementwise calls under bee2bee/hf.py:42-43.
+#include "kernels.h"
+
+#include "common.cuh"
+
+namespace b2b {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (l == 0) sh[0] = r;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+// out[t] = (residual[t] +) norm(x[t]) * (gamma (+1 if gemma))   one CTA per token
+__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                               const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                               float* __restrict__ rstd_out, int h, float eps, int gemma_plus_one) {
+  __shared__ float sh[32];
+  const int t = blockIdx.x;
+  const uint4* row = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * h);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+    uint4 v = row[i];
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(p[j]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  ss = block_sum(ss, sh);
+  const float rs = rsqrtf(ss / h + eps);
+  if (rstd_out != nullptr && threadIdx.x == 0) rstd_out[t] = rs;
+  if (out == nullptr) return;
+  const uint4* grow = reinterpret_cast<const uint4*>(gamma);
+  const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + static_cast<size_t>(t) * h) : nullptr;
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * h);
+  for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+    uint4 v = row[i], g = grow[i], r = rrow ? rrow[i] : make_uint4(0, 0, 0, 0), o;
+    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
+    const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&r);
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(pv[j]), gg = __bfloat1622float2(pg[j]), rr = __bfloat1622float2(pr[j]);
+      if (gemma_plus_one) { gg.x += 1.f; gg.y += 1.f; }
+      po[j] = __floats2bfloat162_rn(f.x * rs * gg.x + rr.x, f.y * rs * gg.y + rr.y);
+    }
+    orow[i] = o;
+  }
+}
+
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                 const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out, int h,
+                                 float eps) {
+  __shared__ float sh[32];
+  const int t = blockIdx.x;
+  const __nv_bfloat16* row = x + static_cast<size_t>(t) * h;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < h; i += blockDim.x) s += __bfloat162float(row[i]);
+  const float mean = block_sum(s, sh) / h;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < h; i += blockDim.x) {
+    float d = __bfloat162float(row[i]) - mean;
+    ss += d * d;
+  }
+  const float rs = rsqrtf(block_sum(ss, sh) / h + eps);
+  for (int i = threadIdx.x; i < h; i += blockDim.x) {
+    float v = (__bfloat162float(row[i]) - mean) * rs * __bfloat162float(gamma[i]) + __bfloat162float(beta[i]);
+    out[static_cast<size_t>(t) * h + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// out[t] = E[ids[t]] * scale (+ P[positions[t]]).  When tok_flag != null the ids were
+// written by the last piece's sampler (peer store) and we acquire the flag first.
+__global__ void embed_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                             const __nv_bfloat16* __restrict__ pos_table, const int* __restrict__ positions,
+                             __nv_bfloat16* __restrict__ out, int h, int vocab, float scale,
+                             const uint32_t* tok_flag, const uint32_t* tok_epoch) {
+  if (tok_flag != nullptr) {
+    if (threadIdx.x == 0) wait_flag_ge(tok_flag, *reinterpret_cast<const volatile uint32_t*>(tok_epoch) + 1);
+    __syncthreads();
+  }
+  const int t = blockIdx.x;
+  int id = *reinterpret_cast<const volatile int*>(ids + t);
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * h);
+  const uint4* psrc = pos_table ? reinterpret_cast<const uint4*>(pos_table + static_cast<size_t>(positions[t]) * h) : nullptr;
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * h);
+  for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+    uint4 v = src[i];
+    if (scale != 1.f || psrc) {
+      uint4 pp = psrc ? psrc[i] : make_uint4(0, 0, 0, 0);
+      __nv_bfloat162* pv = reinterpret_cast<__nv_bfloat162*>(&v);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(pv[j]), q = __bfloat1622float2(p2[j]);
+        // HF rounds the scaled embedding to bf16 before adding anything else
+        pv[j] = __floats2bfloat162_rn(bf16_round(f.x * scale) + q.x, bf16_round(f.y * scale) + q.y);
+      }
+    }
+    dst[i] = v;
+  }
+}
+
+// Unfused KV append (GPT-2 path): qkv [T, q_dim + 2*kv_dim] -> q_out, paged K/V.
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+                                 __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                                 const int* __restrict__ slots, int q_dim, int kv_dim, float q_scale) {
+  const int t = blockIdx.x;
+  const int tot = q_dim + 2 * kv_dim;
+  const int slot = slots[t];
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const __nv_bfloat16 v = qkv[static_cast<size_t>(t) * tot + i];
+    if (i < q_dim) q_out[static_cast<size_t>(t) * q_dim + i] = __float2bfloat16_rn(__bfloat162float(v) * q_scale);
+    else if (slot >= 0) {
+      if (i < q_dim + kv_dim) k_cache[static_cast<size_t>(slot) * kv_dim + (i - q_dim)] = v;
+      else v_cache[static_cast<size_t>(slot) * kv_dim + (i - q_dim - kv_dim)] = v;
+    }
+  }
+}
+
+// y = a + b (residual add for unfused paths), 128-bit
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           __nv_bfloat16* __restrict__ out, size_t n8) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n8) return;
+  uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i], o;
+  const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&x);
+  const __nv_bfloat162* py = reinterpret_cast<const __nv_bfloat162*>(&y);
+  __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __bfloat1622float2(px[j]), g = __bfloat1622float2(py[j]);
+    po[j] = __floats2bfloat162_rn(f.x + g.x, f.y + g.y);
+  }
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// Stand-alone handoff primitives (used by the unfused / cudaMemcpyPeer comparator path)
+__global__ void flag_wait_kernel(const uint32_t* flag, const uint32_t* epoch, uint32_t delta) {
+  wait_flag_ge(flag, *reinterpret_cast<const volatile uint32_t*>(epoch) + delta);
+}
+__global__ void flag_signal_kernel(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag) {
+  __threadfence_system();
+  if (flag != nullptr) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch) + 1;
+    *reinterpret_cast<volatile uint32_t*>(epoch) = e;
+    st_release_sys(flag, e);
+  }
+  if (bump_epoch != nullptr) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(bump_epoch) + 1;
+    *reinterpret_cast<volatile uint32_t*>(bump_epoch) = e;
+    if (ack_flag != nullptr) st_release_sys(ack_flag, e);
+  }
+}
+
+// Device-side bookkeeping of a decode step (keeps CUDA-graph replays host-free):
+// positions += 1, kv_len += 1, slot = page(pos) * 64 + pos % 64 for every active sequence.
+__global__ void decode_advance_kernel(int* positions, int* kv_len, int* slots, const int* q_len,
+                                      const int* block_table, int max_pages, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (q_len[i] <= 0) { slots[i] = -1; return; }
+  const int pos = positions[i] + 1;
+  positions[i] = pos;
+  kv_len[i] = pos + 1;
+  const int pg = pos / 64;
+  slots[i] = (pg < max_pages) ? block_table[static_cast<size_t>(i) * max_pages + pg] * 64 + (pos % 64) : -1;
+}
+
+// ------------------------------------------------------------------ launchers
+int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
+                          int max_pages, int n, cudaStream_t s) {
+  decode_advance_kernel<<<(n + 127) / 128, 128, 0, s>>>(positions, kv_len, slots, q_len, block_table, max_pages, n);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_rmsnorm(const void* x, const void* gamma, const void* residual, void* out, float* rstd_out, int tokens,
+                   int h, float eps, int gemma_plus_one, cudaStream_t s) {
+  if (h % 8) return -2;
+  const int threads = h >= 4096 ? 512 : 256;
+  rmsnorm_kernel<<<tokens, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
+                                            static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out),
+                                            rstd_out, h, eps, gemma_plus_one);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_layernorm(const void* x, const void* gamma, const void* beta, void* out, int tokens, int h, float eps,
+                     cudaStream_t s) {
+  layernorm_kernel<<<tokens, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
+                                          static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), h, eps);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_embed(const int* ids, const void* table, const void* pos_table, const int* positions, void* out, int tokens,
+                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, cudaStream_t s) {
+  if (h % 8) return -2;
+  embed_kernel<<<tokens, 256, 0, s>>>(ids, static_cast<const __nv_bfloat16*>(table),
+                                      static_cast<const __nv_bfloat16*>(pos_table), positions,
+                                      static_cast<__nv_bfloat16*>(out), h, vocab, scale, tok_flag, tok_epoch);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int* slots, int tokens,
+                     int q_dim, int kv_dim, float q_scale, cudaStream_t s) {
+  kv_append_kernel<<<tokens, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out),
+                                          static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache),
+                                          slots, q_dim, kv_dim, q_scale);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
+  if (n % 8) return -2;
+  const size_t n8 = n / 8;
+  add_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a),
+                                                                      static_cast<const __nv_bfloat16*>(b),
+                                                                      static_cast<__nv_bfloat16*>(out), n8);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s) {
+  flag_wait_kernel<<<1, 1, 0, s>>>(flag, epoch, delta);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_flag_signal(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag, cudaStream_t s) {
+  flag_signal_kernel<<<1, 1, 0, s>>>(flag, epoch, bump_epoch, ack_flag);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace b2b

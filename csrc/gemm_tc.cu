@@ -1,0 +1,496 @@
+// tcgen05 / TMEM / TMA "swap-AB" GEMM for sm_100a.
+//
+//   out[t, n] = epilogue( sum_k X[t, k] * W[n, k] )
+//
+// The WEIGHT matrix is the 128-row MMA "A" operand (UMMA_M = 128 output features
+// per CTA, one TMEM lane per feature) and the TOKENS are the MMA "N" dimension
+// (BN = 16..256 TMEM columns).  Decode batches of 1..32 tokens therefore cost
+// 16..32 tensor-core columns instead of a padded 128-row tile, the kernel streams
+// W exactly once through a TMA -> smem ring, and the whole op sits on the HBM
+// roofline.  Small problems get their parallelism from split-K across a
+// thread-block cluster whose partial accumulators are reduced through DSMEM.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global / peer).
+//
+// Fused epilogues: residual add, SwiGLU/GeGLU, bias+GELU, RMSNorm scale of the
+// *input* (gamma folded into W; per-token 1/rms computed by the idle epilogue
+// warps during the main loop), RoPE + paged-KV append for the QKV projection,
+// and the NVLink piece handoff: the tail GEMM of piece i stores its tiles straight
+// into piece i+1's input buffer on the peer GPU and publishes a release flag; the
+// head GEMM of piece i+1 prefetches its weight tiles, acquires the flag, then
+// TMA-loads the freshly written activations.
+//
+// Reference parity: replaces the JSON/WebSocket hidden-state hop of
+// bee2bee/node.py:249-277 and the cuBLAS calls under bee2bee/hf.py:42-43.
+#include "gemm_tc.cuh"
+
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace b2b {
+
+constexpr int BM = 128;   // weight rows per CTA == UMMA_M
+constexpr int BK = 64;    // bf16 elements per 128B swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN <= 32) ? 5 : (BN == 64 ? 4 : (BN == 128 ? 6 : 4));
+  static constexpr int kStageBytes = A_STAGE_BYTES + BN * BK * 2;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                      const __grid_constant__ CUtensorMap tmap_x,
+                                                      const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGE_BYTES = Cfg::kStageBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x;             // 128-row block of W
+  const int tok0 = blockIdx.y * BN;          // first token of this CTA
+  const int splitk = p.splitk;
+  const int krank = (splitk > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = (krank == 0);
+
+  const int nkb_total = p.k / BK;
+  const int kb_begin = static_cast<int>((static_cast<long long>(nkb_total) * krank) / splitk);
+  const int kb_end = static_cast<int>((static_cast<long long>(nkb_total) * (krank + 1)) / splitk);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_w = l2_policy_evict_first();   // weights: streamed once
+      const uint64_t pol_x = l2_policy_evict_last();    // activations: re-read by every CTA
+      int kb = 0;
+      if (p.wait_flag != nullptr) {
+        // Piece-head: start pulling weight tiles before the upstream piece has
+        // delivered its activations, then acquire the handoff flag.
+        const int npre = nkb < STAGES ? nkb : STAGES;
+        for (int i = 0; i < npre; ++i) {
+          mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+          tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BK,
+                           tile_n * BM, pol_w);
+        }
+        const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
+        wait_flag_ge(p.wait_flag, target);
+        fence_proxy_async_all();   // peer-written (generic proxy) data -> TMA (async proxy) reads
+        for (int i = 0; i < npre; ++i) {
+          tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i],
+                           (kb_begin + i) * BK, tok0, pol_x);
+        }
+        kb = npre;
+      }
+      for (; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BK,
+                         tile_n * BM, pol_w);
+        tma_load_2d_hint(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[s],
+                         (kb_begin + kb) * BK, tok0, pol_x);
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                    // frees the smem slot when the MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full_bar); // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------- epilogue warps: prologue work
+    const int et = threadIdx.x - 64;   // 0..127
+    if (leader) {
+      if (p.norm_src != nullptr) {
+        if (p.wait_flag != nullptr) {
+          const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
+          wait_flag_ge(p.wait_flag, target);
+        }
+        // one warp per token: sum of squares of the raw input row (bf16 -> fp32)
+        for (int t = warp - 2; t < BN; t += 4) {
+          const int tok = tok0 + t;
+          float ss = 0.f;
+          if (tok < p.m_tok) {
+            const uint4* row = reinterpret_cast<const uint4*>(p.norm_src + static_cast<size_t>(tok) * p.k);
+            for (int i = lane; i < p.k / 8; i += 32) {
+              uint4 v = row[i];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(h[j]);
+                ss += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          if (lane == 0) rstd_s[t] = (tok < p.m_tok) ? rsqrtf(ss / static_cast<float>(p.k) + p.eps) : 0.f;
+        }
+      } else {
+        for (int t = et; t < BN; t += 128) {
+          const int tok = tok0 + t;
+          rstd_s[t] = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
+        }
+      }
+      epi_bar_sync();
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+  }
+
+  // ------------------------------------------------ split-K reduce through DSMEM
+  // After barrier #1 every CTA's main loop has retired, so the leader's stage ring
+  // is free and is reused as the landing zone for the peers' partial accumulators.
+  float* red = reinterpret_cast<float*>(smem);   // [splitk-1][BN][128]
+  const int q = warp & 3;
+  const int row = q * 32 + lane;                 // TMEM lane == weight row within the tile
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  if (splitk > 1) {
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (warp >= 2 && !leader) {
+      const uint32_t remote = mapa_smem(smem_u32(red), 0) +
+                              static_cast<uint32_t>(((krank - 1) * BN * BM + row) * 4);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st_dsmem_f32(remote + static_cast<uint32_t>((c + i) * BM * 4), v[i]);
+      }
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  }
+
+  // ------------------------------------------------------------ fused epilogue
+  if (warp >= 2 && leader) {
+    const int n_glob = tile_n * BM + row;
+    float* xch = red + (splitk - 1) * BN * BM;   // GLU exchange buffer [BN][64]
+    const float bias_v = (p.bias != nullptr) ? p.bias[n_glob] : 0.f;
+
+    if (p.free_flag != nullptr) {
+      // back-pressure: the consumer must have drained the previous payload of this slot
+      const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(p.signal_epoch);
+      wait_flag_ge(p.free_flag, e);
+    }
+
+    // QKV section bookkeeping (uniform per CTA)
+    int sect = 0, f_in_sect = 0;
+    float inv_freq = 0.f;
+    const int q_dim = p.n_q_heads * p.head_dim, kv_dim = p.n_kv_heads * p.head_dim;
+    if (p.epi == EPI_QKV_ROPE) {
+      const int f = n_glob;
+      sect = (f < q_dim) ? 0 : (f < q_dim + kv_dim ? 1 : 2);
+      f_in_sect = f - (sect == 0 ? 0 : (sect == 1 ? q_dim : q_dim + kv_dim));
+      if (sect < 2 && p.rope_theta > 0.f) {
+        const int j = (f_in_sect % p.head_dim) >> 1;   // rotary pair index (rows are pair-interleaved)
+        inv_freq = exp2f(-(2.f * j / static_cast<float>(p.head_dim)) * log2f(p.rope_theta));
+      }
+    }
+
+    if (p.epi == EPI_GLU) {
+      // phase A: the "up" half (rows 64..127) parks its values in shared memory
+      if (row >= 64) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          for (int r = 0; r < splitk - 1; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += red[(r * BN + c + i) * BM + row];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xch[(c + i) * 64 + (row - 64)] = v[i];
+        }
+      }
+      epi_bar_sync();
+    }
+
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      if (p.epi == EPI_GLU && row >= 64) break;
+      if (tok0 + c >= p.m_tok) break;
+      float v[16];
+      tmem_ld16(taddr + c, v);
+      for (int r = 0; r < splitk - 1; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += red[(r * BN + c + i) * BM + row];
+
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int tok = tok0 + c + i;
+        const bool valid = tok < p.m_tok;
+        const float rs = rstd_s[c + i];
+        float a = v[i] * rs + bias_v;
+        switch (p.epi) {
+          case EPI_PLAIN: {
+            if (valid) {
+              if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = a;
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = __float2bfloat16_rn(a);
+            }
+          } break;
+          case EPI_GELU: {
+            if (valid)
+              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
+                  __float2bfloat16_rn(gelu_tanh(a));
+          } break;
+          case EPI_RESIDUAL: {
+            if (valid) {
+              const float r = __bfloat162float(p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob]);
+              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
+                  __float2bfloat16_rn(a + r);
+            }
+          } break;
+          case EPI_GLU: {
+            const float u = xch[(c + i) * 64 + row] * rs;
+            const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
+            if (valid)
+              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
+                  __float2bfloat16_rn(g * u);
+          } break;
+          case EPI_QKV_ROPE: {
+            float o = a;
+            if (sect < 2 && p.rope_theta > 0.f) {
+              // lanes (2j, 2j+1) hold (x_j, x_{j+hd/2}) thanks to the offline row interleave
+              const float partner = __shfl_xor_sync(0xffffffffu, a, 1);
+              float sn, cs;
+              const float ang = (valid ? static_cast<float>(p.positions[tok]) : 0.f) * inv_freq;
+              sincosf(ang, &sn, &cs);
+              o = (lane & 1) ? (a * cs + partner * sn) : (a * cs - partner * sn);
+            }
+            if (valid) {
+              if (sect == 0) {
+                p.q_out[static_cast<size_t>(tok) * q_dim + f_in_sect] = __float2bfloat16_rn(o * p.q_scale);
+              } else {
+                const int slot = p.slots[tok];
+                __nv_bfloat16* dst = (sect == 1 ? p.k_cache : p.v_cache);
+                if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
+              }
+            }
+          } break;
+        }
+      }
+    }
+
+    // ------------------------------------------------ handoff publication
+    if (p.signal_flag != nullptr || p.bump_epoch != nullptr) {
+      __threadfence_system();            // my (possibly peer-directed) stores are performed
+      epi_bar_sync();
+      if (threadIdx.x == 64) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        const uint32_t prev = atomicAdd(p.done_counter, 1u);
+        if (prev == total - 1) {
+          __threadfence_system();
+          *p.done_counter = 0;
+          if (p.signal_flag != nullptr) {
+            const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) + 1;
+            *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) = e;
+            st_release_sys(p.signal_flag, e);
+          }
+          if (p.bump_epoch != nullptr) {
+            const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.bump_epoch) + 1;
+            *reinterpret_cast<volatile uint32_t*>(p.bump_epoch) = e;
+            if (p.ack_flag != nullptr) st_release_sys(p.ack_flag, e);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ============================================================== host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] (row stride ld elements), box = [box_rows, 64], 128B swizzle.
+static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows) {
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  Key key{ptr, rows, cols, ld, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *m = it->second; return 0; }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return static_cast<int>(r);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *m;
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = p.splitk;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tw, tx, p));
+}
+
+template <int BN>
+static int set_attr_bn() {
+  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               GemmCfg<BN>::kSmemBytes));
+}
+// Opt every instantiation into its dynamic shared memory size up front (so the first real
+// launch may happen inside a CUDA-graph capture).
+int gemm_tc_init() {
+  int r = 0;
+  if ((r = set_attr_bn<16>())) return r;
+  if ((r = set_attr_bn<32>())) return r;
+  if ((r = set_attr_bn<64>())) return r;
+  if ((r = set_attr_bn<128>())) return r;
+  if ((r = set_attr_bn<256>())) return r;
+  return get_encode() ? 0 : -1;
+}
+
+int gemm_tc_max_splitk(int bn, int epi) {
+  // partial tiles land in the leader's stage ring: (S-1)*BN*512 B (+ GLU exchange BN*256 B)
+  int stages, stage_bytes;
+  switch (bn) {
+    case 16: stages = GemmCfg<16>::kStages; stage_bytes = GemmCfg<16>::kStageBytes; break;
+    case 32: stages = GemmCfg<32>::kStages; stage_bytes = GemmCfg<32>::kStageBytes; break;
+    case 64: stages = GemmCfg<64>::kStages; stage_bytes = GemmCfg<64>::kStageBytes; break;
+    case 128: stages = GemmCfg<128>::kStages; stage_bytes = GemmCfg<128>::kStageBytes; break;
+    default: stages = GemmCfg<256>::kStages; stage_bytes = GemmCfg<256>::kStageBytes; break;
+  }
+  int budget = stages * stage_bytes - (epi == EPI_GLU ? bn * 256 : 0);
+  int s = 1 + budget / (bn * 512);
+  return s > 8 ? 8 : (s < 1 ? 1 : s);
+}
+
+int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn, cudaStream_t stream) {
+  GemmParams p = p_in;
+  if (p.n_out % BM != 0 || p.k % BK != 0 || p.m_tok <= 0) return -2;
+  if (p.splitk < 1) p.splitk = 1;
+  if (p.splitk > 8) p.splitk = 8;
+  const int smax = gemm_tc_max_splitk(bn, p.epi);
+  if (p.splitk > smax) p.splitk = smax;
+  if (p.splitk > p.k / BK) p.splitk = p.k / BK;
+  CUtensorMap tw, tx;
+  int r = make_tmap_bf16(&tw, w, p.n_out, p.k, p.k, BM);
+  if (r) return r;
+  r = make_tmap_bf16(&tx, x, p.m_tok, p.k, p.k, bn);
+  if (r) return r;
+  switch (bn) {
+    case 16: return launch_bn<16>(p, tw, tx, stream);
+    case 32: return launch_bn<32>(p, tw, tx, stream);
+    case 64: return launch_bn<64>(p, tw, tx, stream);
+    case 128: return launch_bn<128>(p, tw, tx, stream);
+    case 256: return launch_bn<256>(p, tw, tx, stream);
+    default: return -3;
+  }
+}
+
+}  // namespace b2b

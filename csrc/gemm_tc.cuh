@@ -1,0 +1,70 @@
+// Parameter block shared by the tcgen05 GEMM kernel and its host launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b2b {
+
+enum GemmEpilogue : int {
+  EPI_PLAIN = 0,      // out = s*acc (+bias)                               -> bf16 or fp32
+  EPI_RESIDUAL = 1,   // out = s*acc (+bias) + residual                    -> bf16 (O-proj / down-proj / piece tail)
+  EPI_GLU = 2,        // rows [0,64) gate, [64,128) up: out = act(g)*u     -> bf16 (SwiGLU / GeGLU)
+  EPI_QKV_ROPE = 3,   // q: rope -> q buffer; k: rope -> paged K; v -> paged V
+  EPI_GELU = 4,       // out = gelu_tanh(s*acc + bias)                     -> bf16 (GPT-2 MLP up)
+};
+
+struct GemmParams {
+  // problem: out[t, n] = epi( sum_k X[t,k] * W[n,k] ),  W is [N, K] row-major (K-major)
+  int m_tok;          // rows of X
+  int n_out;          // rows of W (multiple of 128)
+  int k;              // multiple of 64
+  int splitk;         // cluster size along grid.z (1..8)
+  int epi;
+  int out_fp32;       // EPI_PLAIN only: write fp32 (logits)
+  int act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
+
+  void* out;          // [m_tok, ld_out]
+  int ld_out;
+  const __nv_bfloat16* residual;  // [m_tok, ld_res]
+  int ld_res;
+  const float* bias;              // [n_out] or null
+
+  // fused RMSNorm of the input: gamma is pre-folded into W, so only the per-token
+  // 1/rms remains; it is either given (rstd) or computed by the epilogue warps
+  // from the raw input rows while the MMA pipeline runs (norm_src).
+  const float* rstd;              // [m_tok] or null
+  const __nv_bfloat16* norm_src;  // [m_tok, k] raw input (same tensor as X) or null
+  float eps;
+
+  // EPI_QKV_ROPE
+  __nv_bfloat16* q_out;           // [m_tok, n_q_heads*head_dim]
+  __nv_bfloat16* k_cache;         // [slots, n_kv_heads, head_dim]
+  __nv_bfloat16* v_cache;
+  const int* positions;           // [m_tok]
+  const int* slots;               // [m_tok] physical KV slot of each token
+  int n_q_heads, n_kv_heads, head_dim;
+  float rope_theta;               // <=0: no rotary
+  float q_scale;                  // folded softmax scale applied to q (1.0 = none)
+
+  // NVLink piece handoff ---------------------------------------------------
+  // consumer side (head-of-piece GEMM): wait until *wait_flag >= *wait_epoch + 1
+  // before touching X / norm_src (weights are prefetched meanwhile).
+  const uint32_t* wait_flag;
+  const uint32_t* wait_epoch;
+  // producer side (tail-of-piece GEMM): `out`/`residual` target may be peer memory.
+  // After every CTA has stored its tile: last CTA publishes epoch+1 to *signal_flag
+  // (st.release.sys on the peer), bumps *signal_epoch, and optionally bumps the
+  // consumer-side epoch of this piece's own input slot + acks the upstream producer.
+  uint32_t* signal_flag;          // peer (or local) flag
+  uint32_t* signal_epoch;         // local: number of handoffs already published on this slot
+  uint32_t* done_counter;         // local, self-resetting
+  const uint32_t* free_flag;      // local: consumer's ack (it has consumed `free_flag` inputs)
+  uint32_t* bump_epoch;           // local: this piece's input-slot epoch (incremented once)
+  uint32_t* ack_flag;             // peer: upstream producer's free_flag for our input slot
+};
+
+// Host launcher (gemm_tc.cu). Returns cudaError_t as int.
+int launch_gemm_tc(const GemmParams& p, const void* w, const void* x, int bn, cudaStream_t stream);
+
+}  // namespace b2b

@@ -1,0 +1,45 @@
+// C launcher API of the hand-written sm_100a kernels (no torch dependency: every .cu
+// compiles in seconds with plain nvcc; csrc/binding.cpp is the only torch-facing file).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b2b {
+
+// elementwise.cu
+int launch_rmsnorm(const void* x, const void* gamma, const void* residual, void* out, float* rstd_out, int tokens,
+                   int h, float eps, int gemma_plus_one, cudaStream_t s);
+int launch_layernorm(const void* x, const void* gamma, const void* beta, void* out, int tokens, int h, float eps,
+                     cudaStream_t s);
+int launch_embed(const int* ids, const void* table, const void* pos_table, const int* positions, void* out, int tokens,
+                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, cudaStream_t s);
+int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int* slots, int tokens,
+                     int q_dim, int kv_dim, float q_scale, cudaStream_t s);
+int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s);
+int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s);
+int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
+                          int max_pages, int n, cudaStream_t s);
+int launch_flag_signal(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag, cudaStream_t s);
+
+// attention.cu
+int launch_attention(const void* q, const void* k_cache, const void* v_cache, void* out, const int* block_table,
+                     const int* q_start, const int* q_len, const int* kv_len, float* ws, int seqs, int max_q,
+                     int max_pages, int n_q, int n_kv, int head_dim, int window, float softcap, int splits,
+                     cudaStream_t s);
+int attn_rows(int G, int QB);
+int attention_init();
+
+// sampler.cu
+int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* peer_tokens, int* history,
+                  const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
+                  const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
+                  const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
+                  cudaStream_t s);
+int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s);
+
+// gemm_tc.cu
+int gemm_tc_max_splitk(int bn, int epi);
+int gemm_tc_init();
+
+}  // namespace b2b

@@ -1,0 +1,273 @@
+// Fused sampler for sm_100a: repetition penalty (seen-token bitmap) -> temperature ->
+// exact top-p via two-level radix histogram of the probability bits -> multinomial draw
+// (or argmax when temperature <= 0).  One CTA per sequence, logits are fp32 [B, V] as
+// written by the lm_head GEMM.  The sampled id is stored locally (token ring, history
+// bitmap) and, on the last piece of a pipeline, straight into piece 0's token buffer on
+// the peer GPU followed by a release flag (4 bytes/sequence over NVLink, no NCCL).
+//
+// Semantics follow the reference's generation defaults (bee2bee/hf.py:91-105):
+// repetition_penalty 1.15, top_p 0.95, do_sample iff temperature > 0, greedy otherwise.
+#include "kernels.h"
+
+#include "common.cuh"
+
+namespace b2b {
+
+constexpr int SAMP_THREADS = 1024;
+constexpr int NBINS = 4096;
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ float penalized(const float* logits, const uint32_t* seen, int i, float pen, float inv_temp,
+                                           float cap) {
+  float l = logits[i];
+  if (cap > 0.f) l = cap * tanhf(l / cap);
+  if (seen != nullptr && ((seen[i >> 5] >> (i & 31)) & 1u)) l = l > 0.f ? l / pen : l * pen;
+  return l * inv_temp;
+}
+
+struct SampleParams {
+  const float* logits;      // [B, V]
+  uint32_t* seen;           // [B, ceil(V/32)] bitmap of ids in the context, or null
+  int* out_tokens;          // [B] local
+  int* peer_tokens;         // [B] on piece 0 (may be == out_tokens / null)
+  int* history;             // [B, hist_stride] token ring (host-visible when mapped), or null
+  const int* hist_pos;      // [B] write index into history (device-side step counter)
+  int* hist_pos_out;        // [B] incremented copy
+  int hist_stride;
+  int vocab;
+  int ld;                   // row stride of logits (vocab padded to a GEMM tile)
+  float softcap;            // final-logit soft-capping (Gemma-2), 0 = off
+  const float* temperature; // [B]
+  const float* top_p;       // [B]
+  const float* rep_penalty; // [B]
+  const uint32_t* seeds;    // [B]
+  const uint32_t* step;     // device step counter (rng stream), may be null
+  uint32_t* signal_flag;    // peer flag (token handoff) or null
+  uint32_t* signal_epoch;   // local epoch for the flag
+  uint32_t* done_counter;   // local, self-resetting
+};
+
+__global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams p) {
+  __shared__ float red_f[32];
+  __shared__ int red_i[32];
+  __shared__ float hist[NBINS];
+  __shared__ float s_bcast[4];
+  __shared__ int s_ib[4];
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = p.vocab;
+  const float* logits = p.logits + static_cast<size_t>(b) * p.ld;
+  const float cap = p.softcap;
+  uint32_t* seen = p.seen ? p.seen + static_cast<size_t>(b) * ((V + 31) / 32) : nullptr;
+  const float temp = p.temperature ? p.temperature[b] : 0.f;
+  const float pen = p.rep_penalty ? p.rep_penalty[b] : 1.f;
+  const float top_p = p.top_p ? p.top_p[b] : 1.f;
+  const bool greedy = !(temp > 0.f);
+  const float inv_temp = greedy ? 1.f : 1.f / temp;
+  const uint32_t* seen_r = (pen != 1.f) ? seen : nullptr;
+
+  // ---- pass 1: max (+ argmax)
+  float mx = -INFINITY; int amx = 0;
+  for (int i = tid; i < V; i += SAMP_THREADS) {
+    const float l = penalized(logits, seen_r, i, pen, inv_temp, cap);
+    if (l > mx) { mx = l; amx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
+    if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
+  }
+  if (lane == 0) { red_f[warp] = mx; red_i[warp] = amx; }
+  __syncthreads();
+  if (warp == 0) {
+    mx = red_f[lane]; amx = red_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
+      if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
+    }
+    if (lane == 0) { s_bcast[0] = mx; s_ib[0] = amx; }
+  }
+  __syncthreads();
+  mx = s_bcast[0];
+  int token = s_ib[0];
+
+  if (!greedy) {
+    // ---- pass 2: level-1 histogram of unnormalised probs e = exp(l - max) in (0, 1]
+    // key = top 12 bits below the sign of the float bits (monotone in e)
+    for (int i = tid; i < NBINS; i += SAMP_THREADS) hist[i] = 0.f;
+    __syncthreads();
+    float zsum = 0.f;
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+      zsum += e;
+      atomicAdd(&hist[__float_as_uint(e) >> 19], e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+    if (lane == 0) red_f[warp] = zsum;
+    __syncthreads();
+    if (warp == 0) {
+      float z = red_f[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+      if (lane == 0) s_bcast[1] = z;
+    }
+    __syncthreads();
+    const float Z = s_bcast[1];
+    const float need = top_p * Z;          // mass that must be covered by the kept set
+
+    // find boundary bin: largest bin index B1 with sum_{bin >= B1} >= need  (warp 0 scans from the top)
+    if (warp == 0) {
+      float carry = 0.f; int found = -1; float above = 0.f;
+      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
+        const float v = hist[base + (31 - lane)];     // lane 0 = highest bin of the chunk
+        float pre = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
+        if (ball) {
+          const int l0 = __ffs(ball) - 1;
+          found = base + (31 - l0);
+          above = carry + __shfl_sync(0xffffffffu, pre, l0) - __shfl_sync(0xffffffffu, v, l0);
+        } else {
+          carry += __shfl_sync(0xffffffffu, pre, 31);
+        }
+      }
+      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_bcast[2] = above; }
+    }
+    __syncthreads();
+    const int B1 = s_ib[1];
+    const float above1 = s_bcast[2];       // mass strictly above the boundary bin
+
+    // ---- pass 3: level-2 histogram inside the boundary bin (next 12 bits)
+    for (int i = tid; i < NBINS; i += SAMP_THREADS) hist[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+      const uint32_t u = __float_as_uint(e);
+      if (static_cast<int>(u >> 19) == B1) atomicAdd(&hist[(u >> 7) & (NBINS - 1)], e);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float carry = above1; int found = -1; float kept = 0.f;
+      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
+        const float v = hist[base + (31 - lane)];
+        float pre = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
+        if (ball) {
+          const int l0 = __ffs(ball) - 1;
+          found = base + (31 - l0);
+          kept = carry + __shfl_sync(0xffffffffu, pre, l0);
+        } else {
+          carry += __shfl_sync(0xffffffffu, pre, 31);
+        }
+      }
+      if (found < 0) { found = 0; kept = carry; }
+      if (lane == 0) { s_ib[2] = found; s_bcast[3] = kept; }
+    }
+    __syncthreads();
+    const uint32_t thr_bits = (static_cast<uint32_t>(B1) << 19) | (static_cast<uint32_t>(s_ib[2]) << 7);
+    const float kept_mass = s_bcast[3];    // total mass of tokens with bits(e) >= thr_bits
+
+    // ---- pass 4: multinomial draw over the kept set, in index order
+    const uint32_t stepv = p.step ? *p.step : 0u;
+    const uint32_t h = hash_u32((p.seeds ? p.seeds[b] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
+    const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float target = u01 * kept_mass;
+    // contiguous chunk per thread
+    const int per = (V + SAMP_THREADS - 1) / SAMP_THREADS;
+    const int i0 = tid * per, i1 = min(V, i0 + per);
+    float mine = 0.f;
+    for (int i = i0; i < i1; ++i) {
+      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+      if (__float_as_uint(e) >= thr_bits) mine += e;
+    }
+    // block exclusive scan of `mine`
+    float pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+    if (lane == 31) red_f[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+      float w = red_f[lane], wp = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, wp, o); if (lane >= o) wp += n; }
+      red_f[lane] = wp - w;     // exclusive warp offsets
+    }
+    if (tid == 0) s_ib[3] = -1;
+    __syncthreads();
+    const float excl = red_f[warp] + pre - mine;
+    if (mine > 0.f && target >= excl && target < excl + mine) {
+      float run = excl; int pick = -1;
+      for (int i = i0; i < i1; ++i) {
+        const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+        if (__float_as_uint(e) >= thr_bits) { run += e; pick = i; if (run > target) break; }
+      }
+      if (pick >= 0) atomicMax(&s_ib[3], pick);
+    }
+    __syncthreads();
+    if (s_ib[3] >= 0) token = s_ib[3];   // else (fp round-off at the far edge): fall back to argmax
+  }
+
+  if (tid == 0) {
+    p.out_tokens[b] = token;
+    if (seen != nullptr) atomicOr(&seen[token >> 5], 1u << (token & 31));
+    if (p.history != nullptr) {
+      const int pos = p.hist_pos[b];
+      if (pos < p.hist_stride) p.history[static_cast<size_t>(b) * p.hist_stride + pos] = token;
+      p.hist_pos_out[b] = pos + 1;
+    }
+    if (p.peer_tokens != nullptr && p.peer_tokens != p.out_tokens) p.peer_tokens[b] = token;
+    if (p.signal_flag != nullptr) {
+      __threadfence_system();
+      const uint32_t prev = atomicAdd(p.done_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence_system();
+        *p.done_counter = 0;
+        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) + 1;
+        *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) = e;
+        st_release_sys(p.signal_flag, e);
+      }
+    }
+  }
+}
+
+// mark prompt tokens in the seen bitmap: ids [n], seq_of [n]
+__global__ void mark_seen_kernel(const int* ids, const int* seq_of, uint32_t* seen, int n, int words, int vocab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int id = ids[i];
+  if (id < 0 || id >= vocab) return;
+  atomicOr(&seen[static_cast<size_t>(seq_of[i]) * words + (id >> 5)], 1u << (id & 31));
+}
+
+int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* peer_tokens, int* history,
+                  const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
+                  const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
+                  const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
+                  cudaStream_t s) {
+  SampleParams p;
+  p.logits = logits; p.seen = seen; p.out_tokens = out_tokens; p.peer_tokens = peer_tokens; p.history = history;
+  p.hist_pos = hist_pos; p.hist_pos_out = hist_pos_out; p.hist_stride = hist_stride; p.vocab = vocab; p.ld = ld; p.softcap = softcap;
+  p.temperature = temperature; p.top_p = top_p; p.rep_penalty = rep_penalty; p.seeds = seeds; p.step = step;
+  p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter;
+  sample_kernel<<<batch, SAMP_THREADS, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s) {
+  if (n <= 0) return 0;
+  mark_seen_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, seq_of, seen, n, (vocab + 31) / 32, vocab);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace b2b

@@ -1,0 +1,84 @@
+"""Whole-piece numerics on the GPU: NativePiece (hand-written kernels, paged KV, fused
+epilogues, CUDA graphs) against the plain-PyTorch fp32 oracle, for every model family."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from bee2bee_b200.engine.core import Engine, SamplingParams  # noqa: E402
+from bee2bee_b200.engine.runner import GpuRunner, SeqInit  # noqa: E402
+from bee2bee_b200.models.config import resolve_config  # noqa: E402
+from bee2bee_b200.models.torch_ref import TorchPiece  # noqa: E402
+from bee2bee_b200.models.weights import init_random  # noqa: E402
+
+
+def _oracle(cfg):
+    t = init_random(cfg, range(cfg.n_layers), True, True, device="cuda", dtype=torch.bfloat16, seed=0)
+    return TorchPiece(cfg, range(cfg.n_layers), True, True, {k: v.float() for k, v in t.items()})
+
+
+def _rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-mistral", "tiny-gemma2", "tiny-gpt2"])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_piece_matches_oracle(name, graphs):
+    cfg = resolve_config(name)
+    torch.manual_seed(0)
+    runner = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=4, groups=1, max_seq_len=512,
+                       max_prefill_tokens=128, seed=0, use_graphs=graphs)
+    oracle = _oracle(cfg)
+    V = cfg.vocab_size
+    prompts = [list(range(5, 5 + 150)), [7, 3, 9], list(range(200, 264))]      # chunked (150 > 128), short, page-exact
+    seqs = [SeqInit(slot=i, prompt=[t % V for t in p], pages=list(range(1 + 8 * i, 9 + 8 * i)), temperature=0.0,
+                    top_p=1.0, repetition_penalty=1.0, seed=i) for i, p in enumerate(prompts)]
+    runner.prefill(seqs)
+    caches = [oracle.new_cache() for _ in seqs]
+    with torch.no_grad():
+        ref_last = []
+        for s, c in zip(seqs, caches):
+            ids = torch.tensor([s.prompt], device="cuda")
+            pos = torch.arange(len(s.prompt), device="cuda")[None]
+            ref_last.append(oracle.forward(ids, pos, c, logits_last_only=True)[0, -1])
+    # the last prefill chunk holds sequences in work-list order; compare through the sampled tokens instead:
+    first = runner.tokens[:3].tolist()
+    for b, r in enumerate(ref_last):
+        top2 = r.topk(2).values
+        if (top2[0] - top2[1]).item() > 0.05 * r.abs().max().item():     # only when the arg-max is not a near-tie
+            assert first[b] == int(r.argmax()), f"first token mismatch for seq {b}"
+    # decode: feed the GPU-sampled token to the oracle, compare full logits every step
+    for step in range(5):
+        fed = runner.tokens[:3].tolist()
+        pos_next = [len(s.prompt) + step for s in seqs]
+        runner.decode(1)
+        runner.sync()
+        got = runner.piece.logits[:3, :V]
+        with torch.no_grad():
+            for b in range(3):
+                ref = oracle.forward(torch.tensor([[fed[b]]], device="cuda"),
+                                     torch.tensor([[pos_next[b]]], device="cuda"), caches[b])[0, -1]
+                if cfg.final_softcap > 0:
+                    g = torch.tanh(got[b] / cfg.final_softcap) * cfg.final_softcap
+                else:
+                    g = got[b]
+                err = _rel_err(g, ref)
+                assert err < 6e-2, f"{name} step {step} seq {b}: rel err {err}"
+    hist, hpos = runner.read_history()
+    assert hpos[:3].tolist() == [6, 6, 6]
+    runner.close()
+
+
+def test_engine_gpu_continuous_batching():
+    eng = Engine("tiny-llama", device="cuda", max_batch=4, max_seq_len=256, decode_burst=4)
+    sp = SamplingParams(max_new_tokens=12, temperature=0.8, ignore_eos=True, seed=3)
+    prompts = [[1, 2, 3, 4, 5], [9, 8, 7], list(range(20, 90)), [4], [5, 6], [7, 8, 9, 10]]   # 6 requests > 4 slots
+    outs = eng.generate(prompts, sp)
+    assert [len(o) for o in outs] == [12] * 6
+    assert all(0 <= t < eng.cfg.vocab_size for o in outs for t in o)
+    # determinism: same seeds -> same tokens
+    eng2 = Engine("tiny-llama", device="cuda", max_batch=4, max_seq_len=256, decode_burst=3)
+    outs2 = eng2.generate(prompts[:2], sp)
+    assert outs2 == outs[:2]
+    eng.close()
+    eng2.close()
