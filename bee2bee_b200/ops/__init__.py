@@ -88,13 +88,25 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
+#: (n_out, k) -> split-K override (tuning / sweeps)
+SPLITK_OVERRIDE = {}
+
+
 def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
-    tiles = (n_out // 128) * ((m_tok + bn - 1) // bn)
-    if tiles >= NUM_SMS:
-        return 1
-    want = max(1, round(2 * NUM_SMS / tiles) if tiles * 2 <= NUM_SMS else 1)
-    want = min(want, 8, max(1, (k // 64) // 4))
-    return max(1, min(want, native().gemm_max_splitk(bn, epi)))
+    """Cluster size along K.  Powers of two only: odd cluster sizes (6, 7) schedule poorly on the
+    GPC grid (ncu: launch__cluster_max_active 22 for size 6 vs 74 for size 4)."""
+    if (n_out, k) in SPLITK_OVERRIDE:
+        want = SPLITK_OVERRIDE[(n_out, k)]
+    else:
+        tiles = (n_out // 128) * ((m_tok + bn - 1) // bn)
+        want = 1
+        while tiles * want * 2 <= 2 * NUM_SMS and want < 8:
+            want *= 2
+    want = min(want, 8, max(1, (k // 64) // 2))
+    cap = native().gemm_max_splitk(bn, epi)
+    while want > cap:
+        want //= 2
+    return max(1, want)
 
 
 def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, epi: int = EPI_PLAIN,

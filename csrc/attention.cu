@@ -13,6 +13,7 @@
 #include "kernels.h"
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace b2b {
 
@@ -43,6 +44,8 @@ struct AttnParams {
 // R = query rows per CTA (G * QB, padded to a multiple of 4), D = head dim
 template <int D, int R>
 __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const AttnParams p, const int G, const int QB) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int DP = D + 8;                      // padded row (bf16) -> conflict-free 16B reads
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* k_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [2][PAGE][DP]
@@ -236,6 +239,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const AttnParams p, c
 // merge split partials: grid (seqs, n_kv), block = R*32 threads? -> one warp per row
 template <int D, int R>
 __global__ void attn_merge_kernel(const AttnParams p, const int G) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int seq = blockIdx.x, kvh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= G) return;
@@ -274,12 +279,10 @@ static int launch_attn_t(const AttnParams& p, int G, int QB, int seqs, int max_q
     set = true;
   }
   dim3 grid(p.splits > 1 ? p.splits : max_qblocks, p.n_kv, seqs);
-  attn_kernel<D, R><<<grid, ATT_THREADS, smem, s>>>(p, G, QB);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(attn_kernel<D, R>, grid, dim3(ATT_THREADS), smem, s, 1, p, G, QB);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (p.splits > 1) {
-    attn_merge_kernel<D, R><<<dim3(seqs, p.n_kv), 32 * ((G + 0) < 1 ? 1 : G), 0, s>>>(p, G);
-    e = cudaGetLastError();
+    e = launch_kernel(attn_merge_kernel<D, R>, dim3(seqs, p.n_kv), dim3(32 * (G < 1 ? 1 : G)), 0, s, 1, p, G);
   }
   return static_cast<int>(e);
 }

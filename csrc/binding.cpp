@@ -6,6 +6,7 @@
 
 #include "gemm_tc.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "peer.h"
 
 using at::Tensor;
@@ -94,6 +95,9 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
   check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
 }
+
+void set_pdl(bool on) { b2b::g_pdl_mode = on ? 1 : 0; }
+bool get_pdl() { return b2b::pdl_enabled(); }
 
 int64_t gemm_max_splitk(int64_t bn, int64_t epi) {
   return b2b::gemm_tc_max_splitk(static_cast<int>(bn), static_cast<int>(epi));
@@ -287,6 +291,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
   m.def("gemm_max_splitk", &gemm_max_splitk);
   m.def("init_kernels", &init_kernels);
+  m.def("set_pdl", &set_pdl);
+  m.def("get_pdl", &get_pdl);
   m.def("rmsnorm", &rmsnorm);
   m.def("layernorm", &layernorm);
   m.def("embed", &embed);

@@ -241,6 +241,11 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t targ
   }
 }
 
+// Programmatic dependent launch: wait for (and see the memory of) all prerequisite grids /
+// allow the dependent grid to start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }

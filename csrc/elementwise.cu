@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace b2b {
 
@@ -34,6 +35,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                                const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
                                float* __restrict__ rstd_out, int h, float eps, int gemma_plus_one) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const int t = blockIdx.x;
   const uint4* row = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * h);
@@ -73,6 +76,8 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out, int h,
                                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const int t = blockIdx.x;
   const __nv_bfloat16* row = x + static_cast<size_t>(t) * h;
@@ -97,6 +102,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, const __nv_bfloat16* _
                              const __nv_bfloat16* __restrict__ pos_table, const int* __restrict__ positions,
                              __nv_bfloat16* __restrict__ out, int h, int vocab, float scale,
                              const uint32_t* tok_flag, const uint32_t* tok_epoch) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (tok_flag != nullptr) {
     if (threadIdx.x == 0) wait_flag_ge(tok_flag, *reinterpret_cast<const volatile uint32_t*>(tok_epoch) + 1);
     __syncthreads();
@@ -128,6 +135,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, const __nv_bfloat16* _
 __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
                                  __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
                                  const int* __restrict__ slots, int q_dim, int kv_dim, float q_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int tot = q_dim + 2 * kv_dim;
   const int slot = slots[t];
@@ -144,6 +153,8 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfl
 // y = a + b (residual add for unfused paths), 128-bit
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ out, size_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n8) return;
   uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i], o;
@@ -160,9 +171,13 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 
 // Stand-alone handoff primitives (used by the unfused / cudaMemcpyPeer comparator path)
 __global__ void flag_wait_kernel(const uint32_t* flag, const uint32_t* epoch, uint32_t delta) {
+  pdl_launch_dependents();
+  pdl_wait();
   wait_flag_ge(flag, *reinterpret_cast<const volatile uint32_t*>(epoch) + delta);
 }
 __global__ void flag_signal_kernel(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   __threadfence_system();
   if (flag != nullptr) {
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch) + 1;
@@ -180,6 +195,8 @@ __global__ void flag_signal_kernel(uint32_t* flag, uint32_t* epoch, uint32_t* bu
 // positions += 1, kv_len += 1, slot = page(pos) * 64 + pos % 64 for every active sequence.
 __global__ void decode_advance_kernel(int* positions, int* kv_len, int* slots, const int* q_len,
                                       const int* block_table, int max_pages, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (q_len[i] <= 0) { slots[i] = -1; return; }
@@ -193,35 +210,35 @@ __global__ void decode_advance_kernel(int* positions, int* kv_len, int* slots, c
 // ------------------------------------------------------------------ launchers
 int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
                           int max_pages, int n, cudaStream_t s) {
-  decode_advance_kernel<<<(n + 127) / 128, 128, 0, s>>>(positions, kv_len, slots, q_len, block_table, max_pages, n);
+  launch_kernel(decode_advance_kernel, dim3((n + 127) / 128), dim3(128), 0, s, 1, positions, kv_len, slots, q_len, block_table, max_pages, n);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_rmsnorm(const void* x, const void* gamma, const void* residual, void* out, float* rstd_out, int tokens,
                    int h, float eps, int gemma_plus_one, cudaStream_t s) {
   if (h % 8) return -2;
   const int threads = h >= 4096 ? 512 : 256;
-  rmsnorm_kernel<<<tokens, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
+  launch_kernel(rmsnorm_kernel, dim3(tokens), dim3(threads), 0, s, 1, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
                                             static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out),
                                             rstd_out, h, eps, gemma_plus_one);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_layernorm(const void* x, const void* gamma, const void* beta, void* out, int tokens, int h, float eps,
                      cudaStream_t s) {
-  layernorm_kernel<<<tokens, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
+  launch_kernel(layernorm_kernel, dim3(tokens), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
                                           static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), h, eps);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_embed(const int* ids, const void* table, const void* pos_table, const int* positions, void* out, int tokens,
                  int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, cudaStream_t s) {
   if (h % 8) return -2;
-  embed_kernel<<<tokens, 256, 0, s>>>(ids, static_cast<const __nv_bfloat16*>(table),
+  launch_kernel(embed_kernel, dim3(tokens), dim3(256), 0, s, 1, ids, static_cast<const __nv_bfloat16*>(table),
                                       static_cast<const __nv_bfloat16*>(pos_table), positions,
                                       static_cast<__nv_bfloat16*>(out), h, vocab, scale, tok_flag, tok_epoch);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int* slots, int tokens,
                      int q_dim, int kv_dim, float q_scale, cudaStream_t s) {
-  kv_append_kernel<<<tokens, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out),
+  launch_kernel(kv_append_kernel, dim3(tokens), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out),
                                           static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache),
                                           slots, q_dim, kv_dim, q_scale);
   return static_cast<int>(cudaGetLastError());
@@ -229,17 +246,17 @@ int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache,
 int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
   if (n % 8) return -2;
   const size_t n8 = n / 8;
-  add_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a),
+  launch_kernel(add_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(a),
                                                                       static_cast<const __nv_bfloat16*>(b),
                                                                       static_cast<__nv_bfloat16*>(out), n8);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s) {
-  flag_wait_kernel<<<1, 1, 0, s>>>(flag, epoch, delta);
+  launch_kernel(flag_wait_kernel, dim3(1), dim3(1), 0, s, 1, flag, epoch, delta);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_flag_signal(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag, cudaStream_t s) {
-  flag_signal_kernel<<<1, 1, 0, s>>>(flag, epoch, bump_epoch, ack_flag);
+  launch_kernel(flag_signal_kernel, dim3(1), dim3(1), 0, s, 1, flag, epoch, bump_epoch, ack_flag);
   return static_cast<int>(cudaGetLastError());
 }
 

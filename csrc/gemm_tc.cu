@@ -31,6 +31,7 @@
 #include <tuple>
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace b2b {
 
@@ -104,31 +105,31 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_launch_dependents();     // the next kernel may start its own set-up / weight prefetch now
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint64_t pol_w = l2_policy_evict_first();   // weights: streamed once
       const uint64_t pol_x = l2_policy_evict_last();    // activations: re-read by every CTA
-      int kb = 0;
+      // Weight tiles depend on no earlier kernel: fill the ring with them first, THEN wait for
+      // the producer of the activations (previous kernel via PDL, upstream piece via its flag).
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < npre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+        tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BK, tile_n * BM, pol_w);
+      }
+      pdl_wait();
       if (p.wait_flag != nullptr) {
-        // Piece-head: start pulling weight tiles before the upstream piece has
-        // delivered its activations, then acquire the handoff flag.
-        const int npre = nkb < STAGES ? nkb : STAGES;
-        for (int i = 0; i < npre; ++i) {
-          mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
-          tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BK,
-                           tile_n * BM, pol_w);
-        }
         const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
         wait_flag_ge(p.wait_flag, target);
         fence_proxy_async_all();   // peer-written (generic proxy) data -> TMA (async proxy) reads
-        for (int i = 0; i < npre; ++i) {
-          tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i],
-                           (kb_begin + i) * BK, tok0, pol_x);
-        }
-        kb = npre;
       }
+      for (int i = 0; i < npre; ++i) {
+        tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i], (kb_begin + i) * BK, tok0,
+                         pol_x);
+      }
+      int kb = npre;
       for (; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   } else {
     // ---------------------------------------- epilogue warps: prologue work
     const int et = threadIdx.x - 64;   // 0..127
+    pdl_wait();                        // everything below reads / writes memory of earlier kernels
     if (leader) {
       if (p.norm_src != nullptr) {
         if (p.wait_flag != nullptr) {
@@ -423,19 +425,8 @@ static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorM
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk);
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p.splitk;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tw, tx, p));
+  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
+                                        dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(p.splitk), tw, tx, p));
 }
 
 template <int BN>

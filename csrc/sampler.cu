@@ -10,6 +10,7 @@
 #include "kernels.h"
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace b2b {
 
@@ -52,6 +53,8 @@ struct SampleParams {
 };
 
 __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red_f[32];
   __shared__ int red_i[32];
   __shared__ float hist[NBINS];
@@ -183,36 +186,52 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
     const uint32_t h = hash_u32((p.seeds ? p.seeds[b] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
     const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float target = u01 * kept_mass;
-    // contiguous chunk per thread
-    const int per = (V + SAMP_THREADS - 1) / SAMP_THREADS;
-    const int i0 = tid * per, i1 = min(V, i0 + per);
+    // one contiguous chunk per WARP, lanes stride by one element -> fully coalesced reads
+    const int cw = ((V + 31) / 32 + 31) & ~31;          // chunk width, multiple of 32
+    const int c0 = warp * cw, c1 = min(V, c0 + cw);
     float mine = 0.f;
-    for (int i = i0; i < i1; ++i) {
+    for (int i = c0 + lane; i < c1; i += 32) {
       const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
       if (__float_as_uint(e) >= thr_bits) mine += e;
     }
-    // block exclusive scan of `mine`
-    float pre = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
-    if (lane == 31) red_f[warp] = pre;
-    __syncthreads();
-    if (warp == 0) {
-      float w = red_f[lane], wp = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, wp, o); if (lane >= o) wp += n; }
-      red_f[lane] = wp - w;     // exclusive warp offsets
-    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);   // warp total
+    if (lane == 0) red_f[warp] = mine;
     if (tid == 0) s_ib[3] = -1;
     __syncthreads();
-    const float excl = red_f[warp] + pre - mine;
-    if (mine > 0.f && target >= excl && target < excl + mine) {
-      float run = excl; int pick = -1;
-      for (int i = i0; i < i1; ++i) {
-        const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
-        if (__float_as_uint(e) >= thr_bits) { run += e; pick = i; if (run > target) break; }
+    // exclusive scan over the 32 warp totals (every warp recomputes it: 32 values)
+    float wtot = red_f[lane], wpre = wtot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, wpre, o); if (lane >= o) wpre += n; }
+    const float my_excl = __shfl_sync(0xffffffffu, wpre - wtot, warp);
+    const float my_tot = __shfl_sync(0xffffffffu, wtot, warp);
+    if (my_tot > 0.f && target >= my_excl && target < my_excl + my_tot) {
+      float run = my_excl;
+      int pick = -1;
+      for (int base = c0; base < c1 && pick < 0; base += 32) {
+        const int i = base + lane;
+        float v = 0.f;
+        if (i < c1) {
+          const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+          if (__float_as_uint(e) >= thr_bits) v = e;
+        }
+        float pre = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && run + pre > target);
+        if (hit) pick = base + (__ffs(hit) - 1);
+        run += __shfl_sync(0xffffffffu, pre, 31);
       }
-      if (pick >= 0) atomicMax(&s_ib[3], pick);
+      if (pick < 0) {                       // round-off at the chunk edge: take the last kept id of the chunk
+        for (int base = ((c1 - 1 - c0) / 32) * 32 + c0; base >= c0 && pick < 0; base -= 32) {
+          const int i = base + lane;
+          bool k = false;
+          if (i < c1) k = __float_as_uint(__expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx)) >= thr_bits;
+          const unsigned m = __ballot_sync(0xffffffffu, k);
+          if (m) pick = base + (31 - __clz(m));
+        }
+      }
+      if (lane == 0 && pick >= 0) atomicMax(&s_ib[3], pick);
     }
     __syncthreads();
     if (s_ib[3] >= 0) token = s_ib[3];   // else (fp round-off at the far edge): fall back to argmax
@@ -243,6 +262,8 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
 
 // mark prompt tokens in the seen bitmap: ids [n], seq_of [n]
 __global__ void mark_seen_kernel(const int* ids, const int* seq_of, uint32_t* seen, int n, int words, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int id = ids[i];
@@ -260,14 +281,13 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
   p.hist_pos = hist_pos; p.hist_pos_out = hist_pos_out; p.hist_stride = hist_stride; p.vocab = vocab; p.ld = ld; p.softcap = softcap;
   p.temperature = temperature; p.top_p = top_p; p.rep_penalty = rep_penalty; p.seeds = seeds; p.step = step;
   p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter;
-  sample_kernel<<<batch, SAMP_THREADS, 0, s>>>(p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_kernel(sample_kernel, dim3(batch), dim3(SAMP_THREADS), 0, s, 1, p));
 }
 
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s) {
   if (n <= 0) return 0;
-  mark_seen_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, seq_of, seen, n, (vocab + 31) / 32, vocab);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_kernel(mark_seen_kernel, dim3((n + 255) / 256), dim3(256), 0, s, 1, ids, seq_of, seen, n,
+                                        (vocab + 31) / 32, vocab));
 }
 
 }  // namespace b2b

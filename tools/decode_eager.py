@@ -14,6 +14,10 @@ r = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=B, groups=1, max_
 seqs = [SeqInit(slot=i, prompt=[(7 + 131 * i + 31 * j) % 100000 + 256 for j in range(16)], pages=[1 + 2 * i, 2 + 2 * i],
                 temperature=0.7, seed=i) for i in range(B)]
 r.prefill(seqs)
+r.decode(2)
+r.sync()
+torch.cuda.profiler.start()
 r.decode(steps)
 r.sync()
+torch.cuda.profiler.stop()
 print("done", r.kernel_launches)
