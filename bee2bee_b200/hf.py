@@ -76,6 +76,7 @@ def load_model_and_tokenizer(model_name: str, device: Optional[str] = None, piec
             tok = load_tokenizer(model_name, cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id)
             lm = LoadedModel(model_name, eng, tok)
             _MODELS[key] = lm
+        lm.engine.start()             # no-op when the scheduler thread is alive; revives a stopped engine
     return lm, lm.tokenizer, str(device)
 
 

@@ -117,7 +117,8 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          n_kv_heads: int = 0, head_dim: int = 0, rope_theta: float = 0.0, q_scale: float = 1.0,
          out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
-         done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0) -> Optional[torch.Tensor]:
+         done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
+         dbg: int = 0) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -139,7 +140,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag)
+                  ack_flag, dbg)
     return out
 
 

@@ -45,7 +45,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, double rope_theta, double q_scale,
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
-          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag) {
+          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg) {
   check_bf16(w, "w");
   check_bf16(x, "x");
   TORCH_CHECK(w.dim() == 2 && x.dim() == 2 && w.size(1) == x.size(1), "gemm: shape mismatch");
@@ -84,6 +84,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.free_flag = as_ptr<const uint32_t>(free_flag);
   p.bump_epoch = as_ptr<uint32_t>(bump_epoch);
   p.ack_flag = as_ptr<uint32_t>(ack_flag);
+  p.dbg = as_ptr<unsigned long long>(dbg);
   if (p.epi == b2b::EPI_QKV_ROPE) {
     TORCH_CHECK(p.q_out && p.k_cache && p.v_cache && p.slots, "qkv epilogue needs q_out/k_cache/v_cache/slots");
     TORCH_CHECK(p.rope_theta <= 0.f || p.positions, "rope needs positions");

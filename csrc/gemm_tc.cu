@@ -54,9 +54,20 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define B2B_DBG(slot)                                                                                          \
+  do {                                                                                                         \
+    if (p.dbg != nullptr)                                                                                      \
+      p.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime();          \
+  } while (0)
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                       const __grid_constant__ CUtensorMap tmap_x,
                                                       const GemmParams p) {
@@ -74,6 +85,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) B2B_DBG(0);
   const int tile_n = blockIdx.x;             // 128-row block of W
   const int tok0 = blockIdx.y * BN;          // first token of this CTA
   const int splitk = p.splitk;
@@ -106,6 +118,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   pdl_launch_dependents();     // the next kernel may start its own set-up / weight prefetch now
+  if (threadIdx.x == 0) B2B_DBG(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -130,6 +143,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                          pol_x);
       }
       int kb = npre;
+      B2B_DBG(2);
       for (; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -150,6 +164,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
+        if (kb == 0) B2B_DBG(3);
         const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES));
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES));
 #pragma unroll
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                    // frees the smem slot when the MMAs retire
-        if (kb == nkb - 1) umma_commit(tmem_full_bar); // accumulator complete
+        if (kb == nkb - 1) { umma_commit(tmem_full_bar); B2B_DBG(4); }   // accumulator complete
       }
       __syncwarp();
     }
@@ -202,12 +217,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) B2B_DBG(5);
   }
 
   // ------------------------------------------------ split-K reduce through DSMEM
   // After barrier #1 every CTA's main loop has retired, so the leader's stage ring
   // is free and is reused as the landing zone for the peers' partial accumulators.
-  float* red = reinterpret_cast<float*>(smem);   // [splitk-1][BN][128]
+  constexpr int RED_LD = BN + 4;
+  float* red = reinterpret_cast<float*>(smem);   // [splitk-1][128 rows][BN + 4]
   const int q = warp & 3;
   const int row = q * 32 + lane;                 // TMEM lane == weight row within the tile
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -215,14 +232,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     cluster_arrive_release();
     cluster_wait_acquire();
     if (warp >= 2 && !leader) {
+      // partial accumulators -> leader's smem, layout [rank][row][BN + 4] (row-padded so that both
+      // the 128-bit DSMEM stores here and the leader's 128-bit reads are bank-conflict free)
       const uint32_t remote = mapa_smem(smem_u32(red), 0) +
-                              static_cast<uint32_t>(((krank - 1) * BN * BM + row) * 4);
+                              static_cast<uint32_t>((((krank - 1) * BM + row) * RED_LD) * 4);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(taddr + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) st_dsmem_f32(remote + static_cast<uint32_t>((c + i) * BM * 4), v[i]);
+        for (int i = 0; i < 16; i += 4)
+          st_dsmem_v4(remote + static_cast<uint32_t>((c + i) * 4), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
       }
     }
     cluster_arrive_release();
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   // ------------------------------------------------------------ fused epilogue
   if (warp >= 2 && leader) {
     const int n_glob = tile_n * BM + row;
-    float* xch = red + (splitk - 1) * BN * BM;   // GLU exchange buffer [BN][64]
+    float* xch = red + (splitk - 1) * BM * RED_LD;   // GLU exchange buffer [BN][64]
     const float bias_v = (p.bias != nullptr) ? p.bias[n_glob] : 0.f;
 
     if (p.free_flag != nullptr) {
@@ -245,7 +265,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     int sect = 0, f_in_sect = 0;
     float inv_freq = 0.f;
     const int q_dim = p.n_q_heads * p.head_dim, kv_dim = p.n_kv_heads * p.head_dim;
-    if (p.epi == EPI_QKV_ROPE) {
+    if constexpr (EPI == EPI_QKV_ROPE) {
       const int f = n_glob;
       sect = (f < q_dim) ? 0 : (f < q_dim + kv_dim ? 1 : 2);
       f_in_sect = f - (sect == 0 ? 0 : (sect == 1 ? q_dim : q_dim + kv_dim));
@@ -255,16 +275,21 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
     }
 
-    if (p.epi == EPI_GLU) {
+    if constexpr (EPI == EPI_GLU) {
       // phase A: the "up" half (rows 64..127) parks its values in shared memory
       if (row >= 64) {
 #pragma unroll 1
         for (int c = 0; c < BN; c += 16) {
           float v[16];
           tmem_ld16(taddr + c, v);
-          for (int r = 0; r < splitk - 1; ++r)
+          for (int r = 0; r < splitk - 1; ++r) {
+            const float4* pr = reinterpret_cast<const float4*>(red + (r * BM + row) * RED_LD + c);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += red[(r * BN + c + i) * BM + row];
+            for (int i = 0; i < 4; ++i) {
+              const float4 q4 = pr[i];
+              v[4 * i] += q4.x; v[4 * i + 1] += q4.y; v[4 * i + 2] += q4.z; v[4 * i + 3] += q4.w;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) xch[(c + i) * 64 + (row - 64)] = v[i];
         }
@@ -274,70 +299,61 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
-      if (p.epi == EPI_GLU && row >= 64) break;
+      if (EPI == EPI_GLU && row >= 64) break;
       if (tok0 + c >= p.m_tok) break;
       float v[16];
       tmem_ld16(taddr + c, v);
-      for (int r = 0; r < splitk - 1; ++r)
+      for (int r = 0; r < splitk - 1; ++r) {
+        const float4* pr = reinterpret_cast<const float4*>(red + (r * BM + row) * RED_LD + c);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += red[(r * BN + c + i) * BM + row];
+        for (int i = 0; i < 4; ++i) {
+          const float4 q4 = pr[i];
+          v[4 * i] += q4.x; v[4 * i + 1] += q4.y; v[4 * i + 2] += q4.z; v[4 * i + 3] += q4.w;
+        }
+      }
 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int tok = tok0 + c + i;
-        const bool valid = tok < p.m_tok;
+        if (tok >= p.m_tok) continue;            // warp-uniform: padded token columns do no work
         const float rs = rstd_s[c + i];
-        float a = v[i] * rs + bias_v;
-        switch (p.epi) {
-          case EPI_PLAIN: {
-            if (valid) {
-              if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = a;
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = __float2bfloat16_rn(a);
-            }
-          } break;
-          case EPI_GELU: {
-            if (valid)
-              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
-                  __float2bfloat16_rn(gelu_tanh(a));
-          } break;
-          case EPI_RESIDUAL: {
-            if (valid) {
-              const float r = __bfloat162float(p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob]);
-              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
-                  __float2bfloat16_rn(a + r);
-            }
-          } break;
-          case EPI_GLU: {
-            const float u = xch[(c + i) * 64 + row] * rs;
-            const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
-            if (valid)
-              reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
-                  __float2bfloat16_rn(g * u);
-          } break;
-          case EPI_QKV_ROPE: {
-            float o = a;
-            if (sect < 2 && p.rope_theta > 0.f) {
-              // lanes (2j, 2j+1) hold (x_j, x_{j+hd/2}) thanks to the offline row interleave
-              const float partner = __shfl_xor_sync(0xffffffffu, a, 1);
-              float sn, cs;
-              const float ang = (valid ? static_cast<float>(p.positions[tok]) : 0.f) * inv_freq;
-              sincosf(ang, &sn, &cs);
-              o = (lane & 1) ? (a * cs + partner * sn) : (a * cs - partner * sn);
-            }
-            if (valid) {
-              if (sect == 0) {
-                p.q_out[static_cast<size_t>(tok) * q_dim + f_in_sect] = __float2bfloat16_rn(o * p.q_scale);
-              } else {
-                const int slot = p.slots[tok];
-                __nv_bfloat16* dst = (sect == 1 ? p.k_cache : p.v_cache);
-                if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
-              }
-            }
-          } break;
+        const float a = v[i] * rs + bias_v;
+        if constexpr (EPI == EPI_PLAIN) {
+          if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = a;
+          else reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = __float2bfloat16_rn(a);
+        } else if constexpr (EPI == EPI_GELU) {
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
+              __float2bfloat16_rn(gelu_tanh(a));
+        } else if constexpr (EPI == EPI_RESIDUAL) {
+          const float r = __bfloat162float(p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob]);
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
+              __float2bfloat16_rn(a + r);
+        } else if constexpr (EPI == EPI_GLU) {
+          const float u = xch[(c + i) * 64 + row] * rs;
+          const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
+              __float2bfloat16_rn(g * u);
+        } else {   // EPI_QKV_ROPE
+          float o = a;
+          if (sect < 2 && p.rope_theta > 0.f) {
+            // lanes (2j, 2j+1) hold (x_j, x_{j+hd/2}) thanks to the offline row interleave
+            const float partner = __shfl_xor_sync(0xffffffffu, a, 1);
+            float sn, cs;
+            sincosf(static_cast<float>(p.positions[tok]) * inv_freq, &sn, &cs);
+            o = (lane & 1) ? (a * cs + partner * sn) : (a * cs - partner * sn);
+          }
+          if (sect == 0) {
+            p.q_out[static_cast<size_t>(tok) * q_dim + f_in_sect] = __float2bfloat16_rn(o * p.q_scale);
+          } else {
+            const int slot = p.slots[tok];
+            __nv_bfloat16* dst = (sect == 1 ? p.k_cache : p.v_cache);
+            if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
+          }
         }
       }
     }
 
+    if (threadIdx.x == 64) B2B_DBG(6);
     // ------------------------------------------------ handoff publication
     if (p.signal_flag != nullptr || p.bump_epoch != nullptr) {
       __threadfence_system();            // my (possibly peer-directed) stores are performed
@@ -369,6 +385,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 0) B2B_DBG(7);
 }
 
 // ============================================================== host side
@@ -415,24 +432,47 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64
   return 0;
 }
 
-template <int BN>
-static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
+template <int BN, int EPI>
+static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
+  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
                                         dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(p.splitk), tw, tx, p));
 }
 
+// one compact kernel per (token tile, epilogue): a runtime `switch` in the 16x-unrolled epilogue
+// loop made the kernel instruction-fetch bound (5.4 us epilogue, see profiles/gemm_timeline.md)
+template <int BN>
+static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_PLAIN: return launch_bn_epi<BN, EPI_PLAIN>(p, tw, tx, stream);
+    case EPI_RESIDUAL: return launch_bn_epi<BN, EPI_RESIDUAL>(p, tw, tx, stream);
+    case EPI_GLU: return launch_bn_epi<BN, EPI_GLU>(p, tw, tx, stream);
+    case EPI_QKV_ROPE: return launch_bn_epi<BN, EPI_QKV_ROPE>(p, tw, tx, stream);
+    case EPI_GELU: return launch_bn_epi<BN, EPI_GELU>(p, tw, tx, stream);
+    default: return -4;
+  }
+}
+
+template <int BN, int EPI>
+static int set_attr_one() {
+  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               GemmCfg<BN>::kSmemBytes));
+}
 template <int BN>
 static int set_attr_bn() {
-  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               GemmCfg<BN>::kSmemBytes));
+  int r = 0;
+  if ((r = set_attr_one<BN, EPI_PLAIN>())) return r;
+  if ((r = set_attr_one<BN, EPI_RESIDUAL>())) return r;
+  if ((r = set_attr_one<BN, EPI_GLU>())) return r;
+  if ((r = set_attr_one<BN, EPI_QKV_ROPE>())) return r;
+  return set_attr_one<BN, EPI_GELU>();
 }
 // Opt every instantiation into its dynamic shared memory size up front (so the first real
 // launch may happen inside a CUDA-graph capture).
@@ -447,7 +487,7 @@ int gemm_tc_init() {
 }
 
 int gemm_tc_max_splitk(int bn, int epi) {
-  // partial tiles land in the leader's stage ring: (S-1)*BN*512 B (+ GLU exchange BN*256 B)
+  // partial tiles land in the leader's stage ring: (S-1)*(BN+4)*512 B (+ GLU exchange BN*256 B)
   int stages, stage_bytes;
   switch (bn) {
     case 16: stages = GemmCfg<16>::kStages; stage_bytes = GemmCfg<16>::kStageBytes; break;
@@ -457,7 +497,7 @@ int gemm_tc_max_splitk(int bn, int epi) {
     default: stages = GemmCfg<256>::kStages; stage_bytes = GemmCfg<256>::kStageBytes; break;
   }
   int budget = stages * stage_bytes - (epi == EPI_GLU ? bn * 256 : 0);
-  int s = 1 + budget / (bn * 512);
+  int s = 1 + budget / ((bn + 4) * 512);
   return s > 8 ? 8 : (s < 1 ? 1 : s);
 }
 

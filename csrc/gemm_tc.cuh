@@ -62,6 +62,9 @@ struct GemmParams {
   const uint32_t* free_flag;      // local: consumer's ack (it has consumed `free_flag` inputs)
   uint32_t* bump_epoch;           // local: this piece's input-slot epoch (incremented once)
   uint32_t* ack_flag;             // peer: upstream producer's free_flag for our input slot
+
+  // optional per-CTA timeline (globaltimer ns) for tuning: 8 slots per CTA, null = off
+  unsigned long long* dbg;
 };
 
 // Host launcher (gemm_tc.cu). Returns cudaError_t as int.

@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 C = ops.native(); C.init_kernels(0)
 t = init_random(cfg, range(NL), False, False, device=dev, dtype=torch.bfloat16)
 results = []
-for B in (32, 1):
+for B in [int(os.environ.get("B", "32"))]:
     piece = NativePiece(cfg, range(NL), False, False, t, dev, max_tokens=64, max_seqs=64, num_pages=B + 2)
     i32 = torch.int32
     meta = BatchMeta(ids=torch.zeros(B, device=dev, dtype=i32), positions=torch.full((B,), 20, device=dev, dtype=i32),
