@@ -41,6 +41,10 @@ class ByteTokenizer:
         bs = bytearray()
         for i in ids:
             i = int(i)
+            if i in (self.bos_id, self.eos_id, self.pad_id) and (i < self.OFFSET or i >= self.OFFSET + 256):
+                if not skip_special:
+                    bs.extend({self.bos_id: b"<bos>", self.eos_id: b"<eos>"}.get(i, b"<pad>"))
+                continue
             if self.OFFSET <= i < self.OFFSET + 256 and self.fold == 256:
                 bs.append(i - self.OFFSET)
             elif self.OFFSET <= i < self.OFFSET + self.fold:

@@ -1,0 +1,185 @@
+"""Engine / model layer on CPU: configs, piece splitting, weights round trip, the torch oracle
+against Hugging Face's own modelling code, tokenizer, scheduler behaviour."""
+import math
+import os
+
+import pytest
+import torch
+
+from bee2bee_b200.engine.core import Engine, SamplingParams
+from bee2bee_b200.engine.kv import OutOfPages, PageAllocator
+from bee2bee_b200.engine.tokenizer import ByteTokenizer, cut_at_stop_words, parse_transcript
+from bee2bee_b200.models.config import PRESETS, ModelConfig, resolve_config, split_layers
+from bee2bee_b200.models.torch_ref import TorchPiece, sample_reference, top_p_keep_mask
+from bee2bee_b200.models.weights import init_random, load_hf_dir, save_hf_dir
+
+
+def test_presets_match_public_architectures():
+    l = resolve_config("meta-llama/Meta-Llama-3-8B")
+    assert (l.n_layers, l.hidden_size, l.n_heads, l.n_kv_heads, l.head_dim, l.ffn_size, l.vocab_size) == \
+        (32, 4096, 32, 8, 128, 14336, 128256)
+    assert 7.9e9 < l.param_count() < 8.1e9
+    g = resolve_config("gemma2:2b")
+    assert (g.n_layers, g.hidden_size, g.head_dim, g.n_heads, g.n_kv_heads) == (26, 2304, 256, 8, 4)
+    assert g.layer_window(0) == 4096 and g.layer_window(1) == 0 and g.attn_softcap == 50.0 and g.post_norms
+    z = resolve_config("HuggingFaceH4/zephyr-7b-beta")
+    assert z.family == "mistral" and z.sliding_window == 4096 and z.vocab_size == 32000
+    d = resolve_config("distilgpt2")
+    assert (d.n_layers, d.hidden_size, d.n_heads, d.head_dim, d.vocab_size) == (6, 768, 12, 64, 50257) and d.bias
+    with pytest.raises(KeyError):
+        resolve_config("no-such-model")
+
+
+def test_split_layers_uneven():
+    assert [len(r) for r in split_layers(26, 4)] == [7, 7, 6, 6]
+    assert [len(r) for r in split_layers(32, 8)] == [4] * 8
+    assert [list(r) for r in split_layers(6, 2)] == [[0, 1, 2], [3, 4, 5]]
+    assert len(split_layers(2, 8)) == 2
+
+
+def test_random_init_is_piece_invariant():
+    cfg = resolve_config("tiny-llama")
+    whole = init_random(cfg, range(4), True, True, seed=3)
+    part = init_random(cfg, range(2, 4), False, True, seed=3)
+    for k, v in part.items():
+        assert torch.equal(v, whole[k]), k
+    assert "embed" not in part and "lm_head" in part
+    assert not torch.equal(init_random(cfg, range(1), True, False, seed=4)["embed"], whole["embed"])
+
+
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-gpt2", "tiny-gemma2", "tiny-mistral"])
+def test_hf_directory_roundtrip(name, tmp_path):
+    cfg = resolve_config(name)
+    t = init_random(cfg, range(cfg.n_layers), True, True, seed=1)
+    save_hf_dir(str(tmp_path), cfg, t, dtype=torch.float32)
+    cfg2 = resolve_config(str(tmp_path))
+    assert (cfg2.family, cfg2.n_layers, cfg2.hidden_size, cfg2.head_dim) == (cfg.family, cfg.n_layers, cfg.hidden_size, cfg.head_dim)
+    back = load_hf_dir(str(tmp_path), cfg2, range(1, 3), False, False)
+    assert back is not None and all(k.startswith(("l1.", "l2.")) for k in back)
+    for k, v in back.items():
+        assert torch.allclose(v, t[k]), k
+
+
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-gpt2", "tiny-gemma2", "tiny-mistral"])
+def test_oracle_matches_transformers(name, tmp_path):
+    """Our plain-torch model == HF's modelling code on the same random weights (validates the
+    oracle every CUDA kernel is tested against)."""
+    transformers = pytest.importorskip("transformers")
+    cfg = resolve_config(name)
+    t = init_random(cfg, range(cfg.n_layers), True, True, seed=2)
+    save_hf_dir(str(tmp_path), cfg, t, dtype=torch.float32)
+    hf = transformers.AutoModelForCausalLM.from_pretrained(str(tmp_path), dtype=torch.float32, attn_implementation="eager").eval()
+    ids = torch.tensor([[5, 9, 2, 77, 130, 8, 41, 3, 3, 250, 17, 99]])
+    pos = torch.arange(ids.shape[1])[None]
+    ours = TorchPiece(cfg, range(cfg.n_layers), True, True, t).forward(ids, pos, None)
+    with torch.no_grad():
+        ref = hf(input_ids=ids).logits
+    assert torch.allclose(ours, ref, atol=2e-4, rtol=2e-3), (ours - ref).abs().max()
+    # incremental decoding through our KV cache reproduces the full-sequence logits
+    piece = TorchPiece(cfg, range(cfg.n_layers), True, True, t)
+    cache = piece.new_cache()
+    a = piece.forward(ids[:, :7], pos[:, :7], cache)
+    b = piece.forward(ids[:, 7:], pos[:, 7:], cache)
+    assert torch.allclose(torch.cat([a, b], 1), ours, atol=2e-4, rtol=2e-3)
+
+
+def test_sliding_window_changes_long_range_attention():
+    cfg = resolve_config("tiny-mistral")           # window 96
+    t = init_random(cfg, range(cfg.n_layers), True, True)
+    piece = TorchPiece(cfg, range(cfg.n_layers), True, True, t)
+    ids = torch.randint(0, cfg.vocab_size, (1, 150))
+    ids2 = ids.clone()
+    ids2[0, 0] = (ids2[0, 0] + 1) % cfg.vocab_size
+    pos = torch.arange(150)[None]
+    a, b = piece.forward(ids, pos, None), piece.forward(ids2, pos, None)
+    assert not torch.allclose(a[0, 50], b[0, 50])          # token 0 is inside the window of position 50
+    # position 149 can still be influenced through stacked layers (4 x 96 > 149) -- but a single layer cannot:
+    one = TorchPiece(cfg, range(1), True, False, t)
+    ha, hb = one.forward(ids, pos, None), one.forward(ids2, pos, None)
+    assert torch.allclose(ha[0, 149], hb[0, 149]) and not torch.allclose(ha[0, 90], hb[0, 90])
+
+
+def test_sampler_reference_semantics():
+    torch.manual_seed(0)
+    logits = torch.randn(4, 300) * 3
+    seen = torch.zeros(4, 300, dtype=torch.bool)
+    assert torch.equal(sample_reference(logits, seen, 0.0, 0.95, 1.15), logits.argmax(-1))    # greedy iff T <= 0
+    top = logits.argmax(-1)
+    seen[torch.arange(4), top] = True
+    pen = sample_reference(logits, seen, 0.0, 1.0, 100.0)
+    assert (pen != top).all()                                   # heavily penalised arg-max loses
+    keep = top_p_keep_mask(logits, 0.7, 0.95)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(50):
+        tok = sample_reference(logits, None, 0.7, 0.95, 1.0, g)
+        assert keep[torch.arange(4), tok].all()
+    p = (logits / 0.7).softmax(-1)
+    assert ((p * keep).sum(-1) >= 0.95 - 1e-6).all() and (keep.sum(-1) < 300).all()
+
+
+def test_byte_tokenizer_and_transcript_helpers():
+    tok = ByteTokenizer(50257, eos_id=50256, bos_id=50256)
+    ids = tok.encode("héllo wörld")
+    assert ids[0] == 50256 and tok.decode(ids) == "héllo wörld"
+    assert tok.decode([70000, 4 + 65]) != ""           # out-of-range ids still render something printable
+    small = ByteTokenizer(384)
+    assert all(0 <= i < 384 for i in small.encode("any text at all"))
+    msgs = parse_transcript("system: be brief\nuser: hi\nthere\nassistant: hello\nuser: bye\nassistant:")
+    assert [m["role"] for m in msgs] == ["system", "user", "assistant", "user"]
+    assert msgs[1]["content"] == "hi\nthere"
+    assert parse_transcript("just text") == [{"role": "user", "content": "just text"}]
+    assert cut_at_stop_words("fine answer\nuser: next") == ("fine answer\n", True)
+    assert cut_at_stop_words("no stop here") == ("no stop here", False)
+    assert "<|assistant|>" in tok.apply_chat_template(msgs)
+
+
+def test_page_allocator():
+    a = PageAllocator(10)
+    assert a.free_pages == 9 and a.pages_for(64) == 1 and a.pages_for(65) == 2
+    p = a.allocate(1, 130)
+    assert len(p) == 3 and 0 not in p
+    assert a.can_allocate(6 * 64) and not a.can_allocate(7 * 64)
+    with pytest.raises(OutOfPages):
+        a.allocate(2, 7 * 64)
+    a.release(1)
+    assert a.free_pages == 9 and a.utilization() == 0.0
+
+
+def test_engine_continuous_batching_and_limits():
+    eng = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64)
+    sp = SamplingParams(max_new_tokens=5, temperature=0.0, ignore_eos=True)
+    prompts = [[1, 2, 3], [4, 5], [6], [7, 8, 9, 10]]            # 4 requests through 2 slots
+    outs = eng.generate(prompts, sp)
+    assert [len(o) for o in outs] == [5, 5, 5, 5]
+    solo = Engine("tiny-llama", device="cpu", max_batch=1, max_seq_len=64)
+    assert solo.generate([prompts[2]], sp)[0] == outs[2]          # batching does not change results
+    # context budget: prompt is truncated from the left, generation clipped
+    long = eng.generate([list(range(100))], SamplingParams(max_new_tokens=50, temperature=0.0, ignore_eos=True))[0]
+    assert 1 <= len(long) <= 50
+    m = eng.metrics()
+    assert m["requests"] == 5 and m["tokens_generated"] == 20 + len(long) and m["running"] == 0
+    assert eng.alloc.free_pages == eng.alloc.num_pages - 1       # every page returned
+
+
+def test_engine_eos_stop_and_streaming_thread():
+    eng = Engine("tiny-gpt2", device="cpu", max_batch=2, max_seq_len=64)
+    first = eng.generate([[3, 4, 5]], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True))[0]
+    stop = first[2]
+    r = eng.generate([[3, 4, 5]], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True,
+                                                 stop_token_ids=(stop,)))[0]
+    assert r == first[:first.index(stop) + 1]
+    got = []
+    eng.start()
+    req = eng.submit([3, 4, 5], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True), on_token=got.append)
+    req.wait(timeout=30)
+    eng.stop()
+    assert got == first and req.finish_reason == "length" and req.ttft_ms > 0
+
+
+def test_seeded_sampling_is_reproducible():
+    sp = SamplingParams(max_new_tokens=8, temperature=0.9, seed=11, ignore_eos=True)
+    a = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64).generate([[1, 2, 3]], sp)
+    b = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64).generate([[1, 2, 3]], sp)
+    c = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64).generate(
+        [[1, 2, 3]], SamplingParams(max_new_tokens=8, temperature=0.9, seed=12, ignore_eos=True))
+    assert a == b and a != c
