@@ -98,10 +98,15 @@ def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
     if (n_out, k) in SPLITK_OVERRIDE:
         want = SPLITK_OVERRIDE[(n_out, k)]
     else:
+        # measured (tools/layer_sweep.py, Llama-3-8B): the split epilogue costs ~3 us, more with wide
+        # token tiles -> aim for ~1 CTA/SM at bn >= 32, ~2 CTAs/SM at bn = 16; >= 16 k-blocks per CTA
         tiles = (n_out // 128) * ((m_tok + bn - 1) // bn)
+        limit = NUM_SMS if bn >= 32 else 2 * NUM_SMS
         want = 1
-        while tiles * want * 2 <= 2 * NUM_SMS and want < 8:
+        while tiles * want * 2 <= limit and want < 8:
             want *= 2
+        while want > 1 and (k // 64) // want < 16:
+            want //= 2
     want = min(want, 8, max(1, (k // 64) // 2))
     cap = native().gemm_max_splitk(bn, epi)
     while want > cap:
