@@ -182,6 +182,10 @@ class NativePiece:
             xn = self.xa[:T]            # layer output buffer (local)
             # ---------------- attention block
             if self.fused_norm:
+                if li == 0 and wait_flag and not inline:
+                    # wide token tiles use a separate 1/rms kernel that reads the peer-written rows:
+                    # acquire the handoff flag first (the GEMM's own wait then passes immediately)
+                    ops.native().flag_wait(wait_flag, wait_epoch, 1)
                 r = None if inline else ops.rstd(x, eps)
                 ops.gemm(self.w[p + "wqkv"], x, epi=ops.EPI_QKV_ROPE, rstd=r, norm_from_x=inline, eps=eps,
                          q_out=self.q_buf, k_cache=self.k_cache[l], v_cache=self.v_cache[l], positions=m.positions,
