@@ -150,8 +150,12 @@ class Engine:
     def __init__(self, model: str = "tiny-llama", cfg: Optional[ModelConfig] = None, device: Optional[str] = None,
                  pieces: int = 1, max_batch: int = 8, max_seq_len: int = 2048, max_prefill_tokens: int = 2048,
                  decode_burst: int = 8, seed: int = 0, runner=None, groups: int = 1, rank: int = 0, world: int = 1,
-                 control_group=None):
+                 control_group=None, plan_sync: bool = False, plan_group=None):
         self.model = model
+        # plan_sync: rank 0 owns the request queue and broadcasts every newly arrived request to the
+        # follower ranks at the top of each step (serving); False = every rank is fed identical
+        # requests by its caller (SPMD benchmark / tests)
+        self.plan_sync, self.plan_group = plan_sync, plan_group
         self.cfg = cfg or resolve_config(model)
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
@@ -222,6 +226,11 @@ class Engine:
         if self._thread is not None:
             self._thread.join(timeout=10)
             self._thread = None
+        if self.world > 1 and self.plan_sync and self.rank == 0:
+            try:                                   # release the followers blocked in the plan broadcast
+                self._sync_plan([])
+            except Exception:
+                pass
 
     def close(self) -> None:
         self.stop()
@@ -248,6 +257,34 @@ class Engine:
                 self._wake.wait(0.05)
                 self._wake.clear()
 
+    def _sync_plan(self, fresh: List[Request]) -> Optional[List[Request]]:
+        """Replicated control plane: rank 0 broadcasts the requests that arrived since the last step
+        (ids, prompt, sampling params); followers materialise mirror Request objects so that every
+        rank takes identical admission / retirement decisions.  Returns None once rank 0 shuts down."""
+        import torch.distributed as dist
+
+        box = [None]
+        if self.rank == 0:
+            box[0] = {"stop": self._stop, "new": [(r.rid, r.prompt_ids, dict(r.params.__dict__)) for r in fresh]}
+        dist.broadcast_object_list(box, src=0, group=self.plan_group)
+        plan = box[0]
+        if plan["stop"]:
+            self._stop = True
+            return None
+        if self.rank == 0:
+            return fresh
+        out = []
+        for rid, ids, sp in plan["new"]:
+            sp["stop_token_ids"] = tuple(sp.get("stop_token_ids") or ())
+            out.append(Request(rid, list(ids), SamplingParams(**sp), t_submit=time.time()))
+        return out
+
+    def follow_forever(self) -> None:
+        """Follower ranks of a serving mesh: mirror rank 0 until it stops."""
+        while not self._stop:
+            if not self.step():
+                time.sleep(0.002)
+
     def _fail_all(self, msg: str) -> None:
         for r in list(self._running.values()) + self._pending:
             r.error = msg
@@ -267,11 +304,17 @@ class Engine:
         from .runner import SeqInit
 
         t0 = time.time()
+        fresh: List[Request] = []
         while True:
             try:
-                self._pending.append(self._waiting.get_nowait())
+                fresh.append(self._waiting.get_nowait())
             except queue.Empty:
                 break
+        if self.world > 1 and self.plan_sync:
+            fresh = self._sync_plan(fresh)
+            if fresh is None:
+                return False
+        self._pending.extend(fresh)
         admitted: List[Request] = []
         still: List[Request] = []
         for r in self._pending:

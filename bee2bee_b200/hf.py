@@ -71,7 +71,15 @@ def load_model_and_tokenizer(model_name: str, device: Optional[str] = None, piec
         lm = _MODELS.get(key)
         if lm is None:
             cfg = resolve_config(model_name)
-            eng = Engine(model_name, cfg=cfg, device=str(device), pieces=pieces, **engine_kw)
+            if pieces > 1 and str(device).startswith("cuda"):
+                # one process per GPU: this process becomes rank 0, followers are spawned
+                from .parallel.launch import build_engine, spawn_followers
+
+                lm_procs = spawn_followers(model_name, pieces, dict(engine_kw))
+                eng = build_engine(model_name, 0, pieces, **engine_kw)
+                eng._followers = lm_procs
+            else:
+                eng = Engine(model_name, cfg=cfg, device=str(device), pieces=pieces, **engine_kw)
             eng.start()
             tok = load_tokenizer(model_name, cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id)
             lm = LoadedModel(model_name, eng, tok)

@@ -38,3 +38,55 @@ def test_two_gpu_pipeline_matches_single_gpu(model):
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 GPUs")
 def test_four_gpu_pipeline_matches_single_gpu():
     assert _run(4, "tiny-llama", 4, 2, 29613) == _run(1, "tiny-llama", 4, 2, 0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_serve_hf_two_pieces_behind_the_http_sidecar(tmp_path):
+    """`bee2bee serve-hf --pieces 2`: rank 0 = mesh node + API + scheduler, rank 1 = spawned follower;
+    greedy /generate must equal the single-GPU server's answer."""
+    import signal
+    import socket
+    import time
+
+    import httpx
+
+    def free_port():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            return s.getsockname()[1]
+
+    def serve_and_ask(pieces):
+        port = free_port()
+        env = dict(os.environ, BEE2BEE_OFFLINE="1", BEE2BEE_HOME=str(tmp_path / f"h{pieces}"), BEE2BEE_LOG_DIR=str(tmp_path))
+        p = subprocess.Popen([sys.executable, "-m", "bee2bee_b200", "serve-hf", "--model", "tiny-llama", "--pieces",
+                              str(pieces), "--api-port", str(port), "--max-batch", "4", "--max-seq-len", "256"],
+                             env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             start_new_session=True)
+        try:
+            t0 = time.time()
+            while True:
+                try:
+                    d = httpx.get(f"http://127.0.0.1:{port}/", timeout=2).json()
+                    if d.get("models"):
+                        break
+                except Exception:
+                    pass
+                assert p.poll() is None, p.stdout.read()[-3000:]
+                assert time.time() - t0 < 300, "server did not come up"
+                time.sleep(1)
+            r = httpx.post(f"http://127.0.0.1:{port}/generate", timeout=120,
+                           json={"prompt": "user: hello mesh", "max_new_tokens": 12, "temperature": 0}).json()
+            assert r["status"] == "ok", r
+            m = httpx.get(f"http://127.0.0.1:{port}/metrics", timeout=10).json()
+            return r["text"], m
+        finally:
+            os.killpg(p.pid, signal.SIGTERM)
+            try:
+                p.wait(timeout=20)
+            except Exception:
+                os.killpg(p.pid, signal.SIGKILL)
+
+    one, _ = serve_and_ask(1)
+    two, metrics = serve_and_ask(2)
+    assert one == two
+    assert metrics["hf"]["tokens_generated"] >= 12
