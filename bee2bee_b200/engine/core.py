@@ -150,7 +150,7 @@ class Engine:
     def __init__(self, model: str = "tiny-llama", cfg: Optional[ModelConfig] = None, device: Optional[str] = None,
                  pieces: int = 1, max_batch: int = 8, max_seq_len: int = 2048, max_prefill_tokens: int = 2048,
                  decode_burst: int = 8, seed: int = 0, runner=None, groups: int = 1, rank: int = 0, world: int = 1,
-                 control_group=None, plan_sync: bool = False, plan_group=None):
+                 control_group=None, plan_sync: bool = False, plan_group=None, quant: str = "bf16"):
         self.model = model
         # plan_sync: rank 0 owns the request queue and broadcasts every newly arrived request to the
         # follower ranks at the top of each step (serving); False = every rank is fed identical
@@ -175,7 +175,7 @@ class Engine:
                                  "rank/world, see bench.py / bee2bee_b200.parallel.launch")
             self.runner = GpuRunner(self.cfg, model, rank, world, self.device, max_batch=max_batch, groups=groups,
                                     max_seq_len=max_seq_len, max_prefill_tokens=max_prefill_tokens, seed=seed,
-                                    control_group=control_group)
+                                    control_group=control_group, quant=quant)
         else:
             self.runner = TorchRunner(self.cfg, model, pieces=pieces, device=self.device, max_batch=max_batch, seed=seed)
         self.gpu = self.device.type == "cuda"

@@ -39,7 +39,7 @@ class GpuRunner:
     def __init__(self, cfg: ModelConfig, model: str = "", rank: int = 0, world: int = 1,
                  device: Optional[torch.device] = None, max_batch: int = 32, groups: int = 1,
                  max_seq_len: int = 4096, max_prefill_tokens: int = 2048, num_pages: int = 0, seed: int = 0,
-                 hist_len: int = 4096, control_group=None, use_graphs: bool = True):
+                 hist_len: int = 4096, control_group=None, use_graphs: bool = True, quant: str = "bf16"):
         assert max_batch % groups == 0, "max_batch must be divisible by the number of micro-batch groups"
         self.cfg, self.rank, self.world = cfg, rank, world
         self.device = torch.device(device if device is not None else f"cuda:{rank}")
@@ -60,7 +60,7 @@ class GpuRunner:
                                dtype=torch.bfloat16, seed=seed)
         max_tokens = max(max_prefill_tokens, self.gb)
         self.piece = NativePiece(cfg, self.layers, self.first, self.last, tensors, self.device, max_tokens,
-                                 max(self.gb, 64), num_pages)
+                                 max(self.gb, 64), num_pages, quant=quant)
         del tensors
         self.mesh = MeshComm(rank, world, self.device, cfg.hidden_size, max_tokens, groups, self.gb, hist_len,
                              control_group)

@@ -66,11 +66,14 @@ class BatchMeta:
 
 class NativePiece:
     def __init__(self, cfg: ModelConfig, layers: Iterable[int], first: bool, last: bool, tensors: Tensors,
-                 device: torch.device, max_tokens: int, max_seqs: int, num_pages: int):
+                 device: torch.device, max_tokens: int, max_seqs: int, num_pages: int, quant: str = "bf16"):
         self.cfg, self.layers, self.first, self.last = cfg, list(layers), first, last
         self.device = torch.device(device)
         self.max_tokens, self.max_seqs, self.num_pages = max_tokens, max_seqs, num_pages
         self.fused_norm = cfg.norm == "rms"
+        # W8A8 e4m3: per-output-row weight scales, per-token dynamic activation scales (Llama / Mistral graphs)
+        self.fp8 = quant == "fp8" and self.fused_norm and not cfg.post_norms and cfg.glu
+        self.wscale: Dict[str, torch.Tensor] = {}
         c = cfg
         assert c.hidden_size % 128 == 0 or c.hidden_size % 64 == 0, "hidden must be a multiple of 64"
         bf = torch.bfloat16
@@ -119,6 +122,14 @@ class NativePiece:
             self.w["lm_head"] = ops.pad_rows(head, 128)
             self.vocab_pad = self.w["lm_head"].shape[0]
         del t
+        if self.fp8:
+            for name in list(self.w):
+                if name.split(".")[-1] in ("wqkv", "wo", "wgu", "w_down") or name == "lm_head":
+                    self.w[name], self.wscale[name] = ops.quantize_weight_fp8(self.w[name])
+            widths = {cfg.hidden_size, cfg.q_dim, cfg.ffn_size}
+            self._qbuf = {k: torch.zeros((max(max_tokens, max_seqs), k), device=self.device, dtype=torch.float8_e4m3fn)
+                          for k in widths}
+            self._qscale = torch.zeros(max(max_tokens, max_seqs), device=self.device, dtype=torch.float32)
 
         # ---- KV cache: one [pages, 64, n_kv, D] pair per layer
         self.k_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
@@ -146,6 +157,11 @@ class NativePiece:
                                    dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
+    def _quant(self, x: torch.Tensor, with_rms: bool):
+        """bf16 rows -> (e4m3 rows, per-token scale [x 1/rms]) in the preallocated staging buffers"""
+        T, K = x.shape
+        return ops.quant_fp8_rows(x, self.cfg.norm_eps, with_rms, out=self._qbuf[K][:T], scale_out=self._qscale[:T])
+
     def weight_bytes(self) -> int:
         return sum(v.numel() * v.element_size() for v in self.w.values())
 
@@ -186,12 +202,19 @@ class NativePiece:
                     # wide token tiles use a separate 1/rms kernel that reads the peer-written rows:
                     # acquire the handoff flag first (the GEMM's own wait then passes immediately)
                     ops.native().flag_wait(wait_flag, wait_epoch, 1)
-                r = None if inline else ops.rstd(x, eps)
-                ops.gemm(self.w[p + "wqkv"], x, epi=ops.EPI_QKV_ROPE, rstd=r, norm_from_x=inline, eps=eps,
-                         q_out=self.q_buf, k_cache=self.k_cache[l], v_cache=self.v_cache[l], positions=m.positions,
-                         slots=m.slots, n_q_heads=c.n_heads, n_kv_heads=c.n_kv_heads, head_dim=c.head_dim,
-                         rope_theta=c.rope_theta, q_scale=c.softmax_scale,
-                         wait_flag=wait_flag if li == 0 else 0, wait_epoch=wait_epoch if li == 0 else 0)
+                qkv_kw = dict(epi=ops.EPI_QKV_ROPE, eps=eps, q_out=self.q_buf, k_cache=self.k_cache[l],
+                              v_cache=self.v_cache[l], positions=m.positions, slots=m.slots, n_q_heads=c.n_heads,
+                              n_kv_heads=c.n_kv_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
+                              q_scale=c.softmax_scale)
+                if self.fp8:
+                    if li == 0 and wait_flag and inline:
+                        ops.native().flag_wait(wait_flag, wait_epoch, 1)     # the quant kernel reads x first
+                    xq, xs = self._quant(x, with_rms=True)
+                    ops.gemm(self.w[p + "wqkv"], xq, rstd=xs, w_scale=self.wscale[p + "wqkv"], **qkv_kw)
+                else:
+                    r = None if inline else ops.rstd(x, eps)
+                    ops.gemm(self.w[p + "wqkv"], x, rstd=r, norm_from_x=inline,
+                             wait_flag=wait_flag if li == 0 else 0, wait_epoch=wait_epoch if li == 0 else 0, **qkv_kw)
             else:
                 if li == 0 and wait_flag:
                     ops.native().flag_wait(wait_flag, wait_epoch, 1)
@@ -206,6 +229,10 @@ class NativePiece:
             if c.post_norms:
                 o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
                 ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
+            elif self.fp8:
+                aq, asc = self._quant(a, with_rms=False)
+                ops.gemm(self.w[p + "wo"], aq, out=x2, epi=ops.EPI_RESIDUAL, residual=x, rstd=asc,
+                         w_scale=self.wscale[p + "wo"])
             else:
                 ops.gemm(self.w[p + "wo"], a, out=x2, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"))
             # ---------------- MLP block
@@ -216,7 +243,11 @@ class NativePiece:
                                bump_epoch=hand.in_epoch, ack_flag=hand.up_ack)
             elif is_tail and out_x is not None:
                 tail_kw = dict(out_ptr=out_x.data_ptr(), ld_out=c.hidden_size)
-            if c.glu:
+            if c.glu and self.fp8:
+                x2q, x2s = self._quant(x2, with_rms=True)
+                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=self.h_buf[:T], epi=ops.EPI_GLU, rstd=x2s,
+                                w_scale=self.wscale[p + "wgu"], act_gelu=(c.act == "gelu_tanh"))
+            elif c.glu:
                 r2 = None
                 if self.fused_norm and not inline:
                     r2 = ops.rstd(x2, eps)
@@ -239,8 +270,13 @@ class NativePiece:
                     ops.rmsnorm(d, self.w[p + "post_ffn_w"], out=tgt, residual=x2, eps=eps, plus_one=c.gemma_norm)
                     xn = tgt
             else:
-                ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL, residual=x2,
-                         bias=self.w.get(p + "b_down"), **tail_kw)
+                if self.fp8:
+                    hq, hs = self._quant(hmid, with_rms=False)
+                    ops.gemm(self.w[p + "w_down"], hq, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
+                             residual=x2, rstd=hs, w_scale=self.wscale[p + "w_down"], **tail_kw)
+                else:
+                    ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
+                             residual=x2, bias=self.w.get(p + "b_down"), **tail_kw)
                 if tail_kw and out_x is not None and not hand.out_x:
                     xn = out_x[:T]
             x = xn
@@ -256,7 +292,11 @@ class NativePiece:
         if not self.first and hand.in_flag:
             # the head GEMM of this piece consumed the input slot; release it to the upstream piece
             ops.native().flag_signal(0, 0, hand.in_epoch, hand.up_ack)
-        if self.fused_norm:
+        if self.fused_norm and self.fp8 and "lm_head" in self.wscale:
+            lq, lsc = self._quant(xl, with_rms=True)
+            ops.gemm(self.w["lm_head"], lq, out=self.logits[:S], epi=ops.EPI_PLAIN, rstd=lsc,
+                     w_scale=self.wscale["lm_head"], out_fp32=True, bn=ops.pick_bn(S))
+        elif self.fused_norm:
             ops.gemm(self.w["lm_head"], xl, out=self.logits[:S], epi=ops.EPI_PLAIN, norm_from_x=True, eps=eps,
                      out_fp32=True, bn=ops.pick_bn(S))
         else:

@@ -123,7 +123,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
-         dbg: int = 0) -> Optional[torch.Tensor]:
+         dbg: int = 0, w_scale: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -145,8 +145,28 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag, dbg)
+                  ack_flag, dbg, w_scale)
     return out
+
+
+# ------------------------------------------------------------------------- fp8
+def quantize_weight_fp8(w: torch.Tensor):
+    """[N, K] -> (e4m3 weights, fp32 per-row scale).  W ~= q * scale[:, None]."""
+    amax = w.float().abs().amax(dim=1).clamp_min(1e-12)
+    scale = (amax / 448.0).float()
+    q = (w.float() / scale[:, None]).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return q.contiguous(), scale.contiguous()
+
+
+def quant_fp8_rows(x: torch.Tensor, eps: float = 1e-5, with_rms: bool = False, out=None, scale_out=None):
+    """Per-token dynamic e4m3 quantisation of a GEMM input; returns (q, scale) where scale already
+    contains 1/rms when ``with_rms`` (RMSNorm fused with gamma folded into the fp8 weights)."""
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float8_e4m3fn)
+    if scale_out is None:
+        scale_out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    native().quant_fp8_rows(x, out, scale_out, eps, with_rms)
+    return out, scale_out
 
 
 # ----------------------------------------------------------------- elementwise

@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=0, help="micro-batch groups in flight (default: N)")
     ap.add_argument("--prompt-len", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="fp8 = W8A8 e4m3 GEMMs (secondary config)")
     return ap.parse_args()
 
 
@@ -128,7 +129,8 @@ def run_ours(args):
     P = args.prompt_len
     max_seq = 1024 if (P + 2 * (K + W) + 64) <= 1024 else P + 2 * (K + W) + 64
     eng = Engine(args.model, cfg=cfg, device=str(dev), max_batch=total, groups=groups, max_seq_len=max_seq,
-                 max_prefill_tokens=max(512, P * min(total, 32)), decode_burst=K, rank=rank, world=world)
+                 max_prefill_tokens=max(512, P * min(total, 32)), decode_burst=K, rank=rank, world=world,
+                 quant=args.dtype)
     runner: GpuRunner = eng.runner
     prompts = synthetic_prompts(total, P, cfg.vocab_size)
 
@@ -211,8 +213,9 @@ def run_ours(args):
         base = baseline_number()
         out = {"metric": "decode_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
                "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": (tok_s / base) if base else None, "dtype": "bf16", "data": "synthetic",
-               "impl": "ours",
+               "vs_baseline": (tok_s / base) if base else None,
+               "dtype": "bf16" if args.dtype == "bf16" else "fp8-e4m3 W8A8 (bf16 KV/attention/residual)",
+               "data": "synthetic", "impl": "ours",
                "config": {"model": args.model, "global_batch": total, "seq_len": P + W + K, "prompt_len": P,
                           "parallelism": f"pp{world}", "pieces": world, "micro_batch_groups": groups,
                           "batch_per_group": B, "weights": "random-init", "sampling": "T=0.7 top_p=0.95 rep=1.15",

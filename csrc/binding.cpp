@@ -45,9 +45,16 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, double rope_theta, double q_scale,
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
-          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg) {
-  check_bf16(w, "w");
-  check_bf16(x, "x");
+          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale) {
+  const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
+  if (fp8) {
+    TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
+                x.is_contiguous(), "fp8 gemm: w and x must be contiguous CUDA float8_e4m3fn");
+    TORCH_CHECK(w_scale.has_value() && w_scale->scalar_type() == at::kFloat, "fp8 gemm needs per-row w_scale (fp32)");
+  } else {
+    check_bf16(w, "w");
+    check_bf16(x, "x");
+  }
   TORCH_CHECK(w.dim() == 2 && x.dim() == 2 && w.size(1) == x.size(1), "gemm: shape mismatch");
   c10::cuda::CUDAGuard guard(w.device());
   b2b::GemmParams p{};
@@ -58,12 +65,15 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.epi = static_cast<int>(epi);
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;
+  p.fp8 = fp8 ? 1 : 0;
+  p.w_scale = ptr_or_null<const float>(w_scale);
   p.out = as_ptr<void>(out_ptr);
   p.ld_out = static_cast<int>(ld_out);
   p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
   p.ld_res = static_cast<int>(ld_res);
   p.bias = ptr_or_null<const float>(bias);
   p.rstd = ptr_or_null<const float>(rstd);
+  TORCH_CHECK(!(fp8 && norm_from_x), "fp8 gemm: pass the combined activation scale through rstd");
   p.norm_src = norm_from_x ? reinterpret_cast<const __nv_bfloat16*>(x.data_ptr()) : nullptr;
   p.eps = static_cast<float>(eps);
   p.q_out = ptr_or_null<__nv_bfloat16>(q_out);
@@ -160,6 +170,18 @@ void add(const Tensor& a, const Tensor& b, const Tensor& out) {
   c10::cuda::CUDAGuard guard(a.device());
   check(b2b::launch_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), static_cast<size_t>(a.numel()), cur_stream()),
         "add");
+}
+
+void quant_fp8_rows(const Tensor& x, const Tensor& q, const Tensor& scale_out, double eps, bool with_rms) {
+  check_bf16(x, "x");
+  TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn && q.is_contiguous() && scale_out.scalar_type() == at::kFloat,
+              "quant_fp8_rows: q must be float8_e4m3fn, scale fp32");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = static_cast<int>(x.size(-1));
+  check(b2b::launch_quant_fp8_rows(x.data_ptr(), q.data_ptr(), reinterpret_cast<float*>(scale_out.data_ptr()),
+                                   static_cast<int>(x.numel() / h), h, static_cast<float>(eps), with_rms ? 1 : 0,
+                                   cur_stream()),
+        "quant_fp8_rows");
 }
 
 void flag_wait(int64_t flag, int64_t epoch, int64_t delta) {
@@ -299,6 +321,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("embed", &embed);
   m.def("kv_append", &kv_append);
   m.def("add", &add);
+  m.def("quant_fp8_rows", &quant_fp8_rows);
   m.def("flag_wait", &flag_wait);
   m.def("flag_signal", &flag_signal);
   m.def("decode_advance", &decode_advance);

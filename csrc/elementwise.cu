@@ -4,6 +4,8 @@
 // Reference parity: the ATen elementwise calls under bee2bee/hf.py:42-43.
 #include "kernels.h"
 
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -169,6 +171,61 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// Per-token dynamic fp8 (e4m3) quantisation of a GEMM input: q = x / s, s = amax / 448.
+// scale_out[t] = s (x optional 1/rms of the row, so a following fp8 GEMM with gamma folded into
+// its weights performs the whole RMSNorm + projection).  One CTA per token.
+__global__ void quant_fp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                      float* __restrict__ scale_out, int h, float eps, int with_rms) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int t = blockIdx.x;
+  const uint4* row = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * h);
+  float amax = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+    uint4 v = row[i];
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(p[j]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  // block max via the sum helper on a monotone transform is awkward: do an explicit max reduce
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) sh[w] = amax;
+  __syncthreads();
+  float m = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (l == 0) sh[0] = m;
+  }
+  __syncthreads();
+  amax = sh[0];
+  __syncthreads();
+  ss = block_sum(ss, sh);
+  const float s = amax > 0.f ? amax / 448.f : 1.f;
+  const float inv = 1.f / s;
+  if (threadIdx.x == 0) scale_out[t] = with_rms ? s * rsqrtf(ss / h + eps) : s;
+  uint2* qrow = reinterpret_cast<uint2*>(q + static_cast<size_t>(t) * h);
+  for (int i = threadIdx.x; i < h / 8; i += blockDim.x) {
+    uint4 v = row[i];
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint8_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(p[j]);
+      o[2 * j] = __nv_cvt_float_to_fp8(f.x * inv, __NV_SATFINITE, __NV_E4M3);
+      o[2 * j + 1] = __nv_cvt_float_to_fp8(f.y * inv, __NV_SATFINITE, __NV_E4M3);
+    }
+    qrow[i] = *reinterpret_cast<uint2*>(o);
+  }
+}
+
 // Stand-alone handoff primitives (used by the unfused / cudaMemcpyPeer comparator path)
 __global__ void flag_wait_kernel(const uint32_t* flag, const uint32_t* epoch, uint32_t delta) {
   pdl_launch_dependents();
@@ -249,6 +306,13 @@ int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s
   launch_kernel(add_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(a),
                                                                       static_cast<const __nv_bfloat16*>(b),
                                                                       static_cast<__nv_bfloat16*>(out), n8);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_quant_fp8_rows(const void* x, void* q, float* scale_out, int tokens, int h, float eps, int with_rms,
+                          cudaStream_t s) {
+  if (h % 8) return -2;
+  launch_kernel(quant_fp8_rows_kernel, dim3(tokens), dim3(h >= 4096 ? 512 : 256), 0, s, 1,
+                static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), scale_out, h, eps, with_rms);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s) {

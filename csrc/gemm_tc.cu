@@ -36,13 +36,14 @@
 namespace b2b {
 
 constexpr int BM = 128;   // weight rows per CTA == UMMA_M
-constexpr int BK = 64;    // bf16 elements per 128B swizzle row
-constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int BK = 64;    // bf16 elements per 128B swizzle row (fp8: 128 elements, same 128 bytes)
+constexpr int ROW_BYTES = 128;
+constexpr int A_STAGE_BYTES = BM * ROW_BYTES;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStages = (BN <= 32) ? 5 : (BN == 64 ? 4 : (BN == 128 ? 6 : 4));
-  static constexpr int kStageBytes = A_STAGE_BYTES + BN * BK * 2;
+  static constexpr int kStageBytes = A_STAGE_BYTES + BN * ROW_BYTES;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4;
 };
@@ -67,7 +68,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool FP8>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                       const __grid_constant__ CUtensorMap tmap_x,
                                                       const GemmParams p) {
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int krank = (splitk > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = (krank == 0);
 
-  const int nkb_total = p.k / BK;
+  constexpr int BKE = FP8 ? 128 : 64;       // K elements per 128-byte k-block
+  const int nkb_total = p.k / BKE;
   const int kb_begin = static_cast<int>((static_cast<long long>(nkb_total) * krank) / splitk);
   const int kb_end = static_cast<int>((static_cast<long long>(nkb_total) * (krank + 1)) / splitk);
   const int nkb = kb_end - kb_begin;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       const int npre = nkb < STAGES ? nkb : STAGES;
       for (int i = 0; i < npre; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
-        tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BK, tile_n * BM, pol_w);
+        tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BKE, tile_n * BM, pol_w);
       }
       pdl_wait();
       if (p.wait_flag != nullptr) {
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         fence_proxy_async_all();   // peer-written (generic proxy) data -> TMA (async proxy) reads
       }
       for (int i = 0; i < npre; ++i) {
-        tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i], (kb_begin + i) * BK, tok0,
+        tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i], (kb_begin + i) * BKE, tok0,
                          pol_x);
       }
       int kb = npre;
@@ -149,15 +151,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BK,
+        tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BKE,
                          tile_n * BM, pol_w);
         tma_load_2d_hint(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[s],
-                         (kb_begin + kb) * BK, tok0, pol_x);
+                         (kb_begin + kb) * BKE, tok0, pol_x);
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
@@ -170,7 +172,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          // one MMA consumes 32 bytes of K per row (16 bf16 / 32 e4m3): +2 in the (addr >> 4) field
+          if constexpr (FP8) umma_f8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          else umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                    // frees the smem slot when the MMAs retire
         if (kb == nkb - 1) { umma_commit(tmem_full_bar); B2B_DBG(4); }   // accumulator complete
@@ -254,6 +258,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const int n_glob = tile_n * BM + row;
     float* xch = red + (splitk - 1) * BM * RED_LD;   // GLU exchange buffer [BN][64]
     const float bias_v = (p.bias != nullptr) ? p.bias[n_glob] : 0.f;
+    // fp8: per-output-row weight scale (the per-token activation scale rides in rstd_s)
+    const float wsc = (FP8 && p.w_scale != nullptr) ? p.w_scale[n_glob] : 1.f;
+    const float wsc_up = (FP8 && EPI == EPI_GLU && p.w_scale != nullptr && row < 64) ? p.w_scale[n_glob + 64] : 1.f;
 
     if (p.free_flag != nullptr) {
       // back-pressure: the consumer must have drained the previous payload of this slot
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int tok = tok0 + c + i;
         if (tok >= p.m_tok) continue;            // warp-uniform: padded token columns do no work
         const float rs = rstd_s[c + i];
-        const float a = v[i] * rs + bias_v;
+        const float a = v[i] * rs * wsc + bias_v;
         if constexpr (EPI == EPI_PLAIN) {
           if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = a;
           else reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = __float2bfloat16_rn(a);
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
               __float2bfloat16_rn(a + r);
         } else if constexpr (EPI == EPI_GLU) {
-          const float u = xch[(c + i) * 64 + row] * rs;
+          const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
               __float2bfloat16_rn(g * u);
@@ -408,22 +415,22 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2D bf16 row-major [rows, cols] (row stride ld elements), box = [box_rows, 64], 128B swizzle.
-static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                          uint32_t box_rows) {
-  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>;
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, int elt_bytes) {
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> g(mu);
-  Key key{ptr, rows, cols, ld, box_rows};
+  Key key{ptr, rows, cols, ld, box_rows, elt_bytes};
   auto it = cache.find(key);
   if (it != cache.end()) { *m = it->second; return 0; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -1;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elt_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(ROW_BYTES / elt_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, elt_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return static_cast<int>(r);
@@ -432,17 +439,17 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64
   return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool FP8>
 static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
+  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI, FP8>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
                                         dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(p.splitk), tw, tx, p));
 }
 
@@ -450,29 +457,34 @@ static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUten
 // loop made the kernel instruction-fetch bound (5.4 us epilogue, see profiles/gemm_timeline.md)
 template <int BN>
 static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
+#define B2B_EPI_CASE(E)                                                                              \
+  case E:                                                                                            \
+    return p.fp8 ? launch_bn_epi<BN, E, true>(p, tw, tx, stream) : launch_bn_epi<BN, E, false>(p, tw, tx, stream);
   switch (p.epi) {
-    case EPI_PLAIN: return launch_bn_epi<BN, EPI_PLAIN>(p, tw, tx, stream);
-    case EPI_RESIDUAL: return launch_bn_epi<BN, EPI_RESIDUAL>(p, tw, tx, stream);
-    case EPI_GLU: return launch_bn_epi<BN, EPI_GLU>(p, tw, tx, stream);
-    case EPI_QKV_ROPE: return launch_bn_epi<BN, EPI_QKV_ROPE>(p, tw, tx, stream);
-    case EPI_GELU: return launch_bn_epi<BN, EPI_GELU>(p, tw, tx, stream);
+    B2B_EPI_CASE(EPI_PLAIN)
+    B2B_EPI_CASE(EPI_RESIDUAL)
+    B2B_EPI_CASE(EPI_GLU)
+    B2B_EPI_CASE(EPI_QKV_ROPE)
+    B2B_EPI_CASE(EPI_GELU)
     default: return -4;
   }
+#undef B2B_EPI_CASE
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool FP8>
 static int set_attr_one() {
-  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                GemmCfg<BN>::kSmemBytes));
 }
 template <int BN>
 static int set_attr_bn() {
   int r = 0;
-  if ((r = set_attr_one<BN, EPI_PLAIN>())) return r;
-  if ((r = set_attr_one<BN, EPI_RESIDUAL>())) return r;
-  if ((r = set_attr_one<BN, EPI_GLU>())) return r;
-  if ((r = set_attr_one<BN, EPI_QKV_ROPE>())) return r;
-  return set_attr_one<BN, EPI_GELU>();
+  if ((r = set_attr_one<BN, EPI_PLAIN, false>()) || (r = set_attr_one<BN, EPI_PLAIN, true>())) return r;
+  if ((r = set_attr_one<BN, EPI_RESIDUAL, false>()) || (r = set_attr_one<BN, EPI_RESIDUAL, true>())) return r;
+  if ((r = set_attr_one<BN, EPI_GLU, false>()) || (r = set_attr_one<BN, EPI_GLU, true>())) return r;
+  if ((r = set_attr_one<BN, EPI_QKV_ROPE, false>()) || (r = set_attr_one<BN, EPI_QKV_ROPE, true>())) return r;
+  if ((r = set_attr_one<BN, EPI_GELU, false>()) || (r = set_attr_one<BN, EPI_GELU, true>())) return r;
+  return 0;
 }
 // Opt every instantiation into its dynamic shared memory size up front (so the first real
 // launch may happen inside a CUDA-graph capture).
@@ -503,16 +515,18 @@ int gemm_tc_max_splitk(int bn, int epi) {
 
 int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn, cudaStream_t stream) {
   GemmParams p = p_in;
-  if (p.n_out % BM != 0 || p.k % BK != 0 || p.m_tok <= 0) return -2;
+  const int elt = p.fp8 ? 1 : 2;
+  const int bke = ROW_BYTES / elt;
+  if (p.n_out % BM != 0 || p.k % bke != 0 || p.m_tok <= 0) return -2;
   if (p.splitk < 1) p.splitk = 1;
   if (p.splitk > 8) p.splitk = 8;
   const int smax = gemm_tc_max_splitk(bn, p.epi);
   if (p.splitk > smax) p.splitk = smax;
-  if (p.splitk > p.k / BK) p.splitk = p.k / BK;
+  if (p.splitk > p.k / bke) p.splitk = p.k / bke;
   CUtensorMap tw, tx;
-  int r = make_tmap_bf16(&tw, w, p.n_out, p.k, p.k, BM);
+  int r = make_tmap(&tw, w, p.n_out, p.k, p.k, BM, elt);
   if (r) return r;
-  r = make_tmap_bf16(&tx, x, p.m_tok, p.k, p.k, bn);
+  r = make_tmap(&tx, x, p.m_tok, p.k, p.k, bn, elt);
   if (r) return r;
   switch (bn) {
     case 16: return launch_bn<16>(p, tw, tx, stream);

@@ -23,6 +23,8 @@ struct GemmParams {
   int epi;
   int out_fp32;       // EPI_PLAIN only: write fp32 (logits)
   int act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
+  int fp8;            // operands are e4m3 (W8A8): W [N,K] and X [T,K] one byte per element
+  const float* w_scale;  // fp8: per-output-row dequant scale [n_out] (activation scale rides in `rstd`)
 
   void* out;          // [m_tok, ld_out]
   int ld_out;

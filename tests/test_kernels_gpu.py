@@ -314,3 +314,35 @@ def test_sampler_padded_vocab_and_softcap():
     ops.sample(buf, out, vocab=V, softcap=30.0)
     capped = torch.tanh(buf[:, :V] / 30.0) * 30.0
     assert out.tolist() == capped.argmax(-1).tolist()
+
+
+# ------------------------------------------------------------------------- fp8
+@pytest.mark.parametrize("m,n,k,splitk", [(1, 256, 512, 1), (20, 384, 1024, 2), (64, 256, 256, 1), (200, 256, 384, 1)])
+def test_gemm_fp8_w8a8(m, n, k, splitk):
+    w, x = bf(n, k, scale=0.05), bf(m, k, scale=2.0)
+    wq, ws = ops.quantize_weight_fp8(w)
+    xq, xs = ops.quant_fp8_rows(x)
+    # quantiser: dequantised values reproduce the input to e4m3 precision, scale = amax / 448
+    close(xq.float() * xs[:, None], x, rtol=7e-2, atol=0.0)
+    assert torch.allclose(xs, x.float().abs().amax(1) / 448, rtol=1e-3)
+    out = ops.gemm(wq, xq, rstd=xs, w_scale=ws, splitk=splitk)
+    ref_q = (xq.float() * xs[:, None]) @ (wq.float() * ws[:, None]).t()      # exact math on the quantised operands
+    close(out, ref_q, rtol=1e-2, atol=1e-2)
+    close(out, x.float() @ w.float().t(), rtol=6e-2, atol=6e-2)              # and close to the bf16 result
+
+
+def test_gemm_fp8_fused_rmsnorm_glu_residual():
+    h, f, m = 512, 256, 9
+    x, gamma, res = bf(m, h, scale=3.0), (1 + 0.1 * torch.randn(h, device="cuda")).to(torch.bfloat16), bf(m, 256)
+    wg, wu, wd = bf(f, h, scale=0.05, seed=1), bf(f, h, scale=0.05, seed=2), bf(256, f, scale=0.05, seed=3)
+    wgu = ops.fold_gamma(ops.glu_interleave_rows(wg, wu), gamma)
+    q, sc = ops.quantize_weight_fp8(wgu)
+    xq, xs = ops.quant_fp8_rows(x, 1e-5, with_rms=True)
+    hmid = ops.gemm(q, xq, epi=ops.EPI_GLU, rstd=xs, w_scale=sc)
+    xn = torch_ref.rms_norm(x.float(), gamma.float(), 1e-5, False)
+    ref_h = torch.nn.functional.silu(xn @ wg.float().t()) * (xn @ wu.float().t())
+    close(hmid, ref_h, rtol=8e-2, atol=8e-2)
+    dq, dsc = ops.quantize_weight_fp8(wd)
+    hq, hs = ops.quant_fp8_rows(hmid)
+    out = ops.gemm(dq, hq, epi=ops.EPI_RESIDUAL, residual=res, rstd=hs, w_scale=dsc)
+    close(out, hmid.float() @ wd.float().t() + res.float(), rtol=8e-2, atol=8e-2)

@@ -82,3 +82,36 @@ def test_engine_gpu_continuous_batching():
     assert outs2 == outs[:2]
     eng.close()
     eng2.close()
+
+
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-mistral"])
+def test_piece_fp8_close_to_oracle(name):
+    """W8A8 e4m3 GEMMs (per-row weight / per-token activation scales): logits stay within fp8 noise of the oracle."""
+    cfg = resolve_config(name)
+    runner = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=4, groups=1, max_seq_len=256,
+                       max_prefill_tokens=128, seed=0, quant="fp8")
+    assert runner.piece.fp8 and runner.piece.w["l0.wqkv"].dtype == torch.float8_e4m3fn
+    oracle = _oracle(cfg)
+    V = cfg.vocab_size
+    prompts = [list(range(5, 45)), [7, 3, 9]]
+    seqs = [SeqInit(slot=i, prompt=[t % V for t in p], pages=[1 + 4 * i, 2 + 4 * i], temperature=0.0, top_p=1.0,
+                    repetition_penalty=1.0, seed=i) for i, p in enumerate(prompts)]
+    runner.prefill(seqs)
+    caches = [oracle.new_cache() for _ in seqs]
+    with torch.no_grad():
+        for s, c in zip(seqs, caches):
+            oracle.forward(torch.tensor([s.prompt], device="cuda"), torch.arange(len(s.prompt), device="cuda")[None], c)
+    for step in range(3):
+        fed = runner.tokens[:2].tolist()
+        runner.decode(1)
+        runner.sync()
+        got = runner.piece.logits[:2, :V]
+        with torch.no_grad():
+            for b in range(2):
+                ref = oracle.forward(torch.tensor([[fed[b]]], device="cuda"),
+                                     torch.tensor([[len(seqs[b].prompt) + step]], device="cuda"), caches[b])[0, -1]
+                err = _rel_err(got[b], ref)
+                assert err < 0.2, f"{name} step {step} seq {b}: rel err {err}"
+                cos = torch.nn.functional.cosine_similarity(got[b].float(), ref.float(), dim=0).item()
+                assert cos > 0.98, cos
+    runner.close()
