@@ -243,7 +243,9 @@ class Engine:
                 "prefill_tokens": self.stats["prefill_tokens"], "decode_steps": self.stats["steps"],
                 "tokens_per_s": self.stats["tokens"] / busy, "running": len(self._running),
                 "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
-                "uptime_s": up}
+                "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
+                "d2h_bytes": self.d2h_bytes, "native_launches": getattr(self.runner, "kernel_launches", 0),
+                "trace": __import__("bee2bee_b200.utils.tracing", fromlist=["TRACER"]).TRACER.summary()}
 
     # --------------------------------------------------------------- scheduler
     def _loop(self) -> None:
@@ -332,7 +334,10 @@ class Engine:
                             repetition_penalty=r.params.repetition_penalty,
                             seed=r.params.seed if r.params.seed is not None else (r.rid * 2654435761) & 0x7FFFFFFF)
                     for r in admitted]
-            self.runner.prefill(seqs)
+            from ..utils.tracing import TRACER
+            with TRACER.range(f"prefill[{len(seqs)} seqs]", getattr(self.runner, "stream", None),
+                              device_timed=self.gpu):
+                self.runner.prefill(seqs)
             for r in admitted:
                 self._running[r.slot] = r
                 self.stats["prefill_tokens"] += len(r.prompt_ids)

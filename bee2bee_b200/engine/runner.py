@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .. import ops
-from ..models.config import ModelConfig, split_layers
+from ..models.config import ModelConfig, balanced_split, split_layers
 from ..models.native import BatchMeta, Handoff, NativePiece
 from ..models.weights import load_or_init
 from ..parallel.mesh import MeshComm
@@ -50,7 +50,7 @@ class GpuRunner:
         self.max_prefill_tokens = max_prefill_tokens
         self.hist_len = hist_len
         self.use_graphs = use_graphs
-        ranges = split_layers(cfg.n_layers, world)
+        ranges = balanced_split(cfg, world)        # the last piece also streams the lm_head: give it fewer layers
         self.layers = list(ranges[rank]) if rank < len(ranges) else []
         self.first, self.last = rank == 0, rank == world - 1
         if num_pages <= 0:
@@ -318,6 +318,11 @@ class GpuRunner:
         """Enqueue ``n_steps`` decode steps for every group (no host synchronisation inside)."""
         if not prepared:
             self.prepare_burst()
+        from ..utils.tracing import TRACER
+        with TRACER.range(f"decode_burst[{n_steps}]", self.stream):
+            self._enqueue_decode(n_steps)
+
+    def _enqueue_decode(self, n_steps: int) -> None:
         with torch.cuda.stream(self.stream):
             for _ in range(n_steps):
                 for g in range(self.groups):

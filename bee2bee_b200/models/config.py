@@ -222,3 +222,22 @@ def split_layers(n_layers: int, pieces: int) -> List[range]:
         out.append(range(start, start + n))
         start += n
     return out
+
+
+def balanced_split(cfg: "ModelConfig", pieces: int) -> List[range]:
+    """Contiguous layer ranges that minimise the heaviest piece when the last piece also streams the
+    lm_head (Llama-3-8B: the 1.05 GB head weighs 2.4 decoder layers) -- the wavefront runs at the pace
+    of its slowest stage.  Falls back to ``split_layers`` when the head is negligible."""
+    pieces = max(1, min(pieces, cfg.n_layers))
+    h, f = cfg.hidden_size, cfg.ffn_size
+    layer = h * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.q_dim * h + (3 if cfg.glu else 2) * h * f
+    head = cfg.vocab_size * h
+    if pieces == 1 or head < 0.5 * layer:
+        return split_layers(cfg.n_layers, pieces)
+    best, best_cost = None, None
+    for last_n in range(1, cfg.n_layers - pieces + 2):
+        rest = split_layers(cfg.n_layers - last_n, pieces - 1)
+        cost = max(max(len(r) for r in rest) * layer, last_n * layer + head)
+        if best_cost is None or cost <= best_cost:     # ties -> the more even split (larger last piece)
+            best, best_cost = rest + [range(cfg.n_layers - last_n, cfg.n_layers)], cost
+    return best
