@@ -88,6 +88,7 @@ class GpuRunner:
         self.seen = torch.zeros((B, (cfg.vocab_size + 31) // 32), device=dev, dtype=i32)
         self.tok_local = torch.zeros(B, device=dev, dtype=i32)     # last rank's own copy of sampled ids
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._pf: Dict[int, dict] = {}             # prefill graphs per token bucket
         self.stream = torch.cuda.Stream(device=dev)
         self.kernel_launches = 0
         self.h2d_bytes = 0
@@ -143,6 +144,10 @@ class GpuRunner:
                 if self.last:
                     ids = torch.tensor(s.prompt, dtype=i32, device=dev)
                     ops.mark_seen(ids, torch.full_like(ids, b), self.seen, self.cfg.vocab_size)
+            if self._prefill_graph_ok(seqs):
+                self._prefill_single_graph(seqs[0])
+                self.stream.synchronize()
+                return
             # pack prompts into chunks of <= max_prefill_tokens tokens
             work: List[Tuple[SeqInit, int, int]] = []          # (seq, start, end)
             for s in seqs:
@@ -174,6 +179,84 @@ class GpuRunner:
                 self.q_len[b] = 1
         self.stream.synchronize()
         self.mesh.barrier()
+
+    # ---- graph-captured prefill for a single short prompt (the common chat / TTFT case) ----------
+    PF_BUCKETS = (16, 32, 64)
+
+    def _prefill_graph_ok(self, seqs) -> bool:
+        return (self.use_graphs and self.world == 1 and len(seqs) == 1 and 0 < len(seqs[0].prompt) <= self.PF_BUCKETS[-1]
+                and self.max_prefill_tokens >= self.PF_BUCKETS[-1])
+
+    def _pf_state(self, tb: int):
+        """Static staging + captured graph for prompts padded to ``tb`` tokens.  One pinned host
+        buffer / one H2D copy carries ids, positions, slots and the scalars."""
+        st = self._pf.get(tb)
+        if st is not None:
+            return st
+        dev, i32 = self.device, torch.int32
+        n = 3 * tb + 8
+        host = torch.zeros(n, dtype=i32).pin_memory()
+        stage = torch.zeros(n, device=dev, dtype=i32)
+        ids, pos, slots = stage[0:tb], stage[tb:2 * tb], stage[2 * tb:3 * tb]
+        qlen, kvlen, row32, last32 = (stage[3 * tb + i:3 * tb + i + 1] for i in range(4))
+        qstart = torch.zeros(1, device=dev, dtype=i32)
+        tok_tmp = torch.zeros(1, device=dev, dtype=i32)
+        st = {"host": host, "stage": stage, "graph": None}
+
+        def body():
+            row = row32.long()
+            meta = BatchMeta(ids=ids, positions=pos, slots=slots, q_start=qstart, q_len=qlen, kv_len=kvlen,
+                             block_table=self.block_table.index_select(0, row), n_tokens=tb, n_seqs=1, max_q=tb,
+                             last_idx=last32.long())
+            out = self.piece.forward(meta)
+            sel = lambda x: x.index_select(0, row)
+            seen_sel = sel(self.seen)
+            ops.sample(out, tok_tmp, seen=seen_sel, temperature=sel(self.temperature), top_p=sel(self.top_p),
+                       rep_penalty=sel(self.rep_pen), seeds=sel(self.seeds), step=self.step_ctr,
+                       vocab=self.cfg.vocab_size, softcap=self.cfg.final_softcap)
+            self.seen.index_copy_(0, row, seen_sel)
+            self.tokens.index_copy_(0, row, tok_tmp)
+            self.history[:, 0].index_copy_(0, row, tok_tmp)
+            self.hist_pos.index_fill_(0, row, 1)
+            self.positions.index_copy_(0, row, kvlen - 1)
+            self.kv_len.index_copy_(0, row, kvlen)
+            self.q_len.index_fill_(0, row, 1)
+
+        saved = (self.seen.clone(), self.tokens.clone(), self.history[:, 0].clone(), self.hist_pos.clone(),
+                 self.positions.clone(), self.kv_len.clone(), self.q_len.clone(), self.step_ctr.clone())
+        with torch.cuda.stream(self.stream):
+            slots.fill_(-1)                         # warm-up run writes no KV
+            qlen.fill_(1); kvlen.fill_(1)
+            body()                                   # eager warm-up (allocations, descriptor cache)
+            self.stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                body()
+        self.stream.synchronize()
+        for dst, src in zip((self.seen, self.tokens, self.history[:, 0], self.hist_pos, self.positions, self.kv_len,
+                             self.q_len, self.step_ctr), saved):
+            dst.copy_(src)
+        torch.cuda.synchronize(self.device)
+        st["graph"] = g
+        self._pf[tb] = st
+        return st
+
+    def _prefill_single_graph(self, s: SeqInit) -> None:
+        L = len(s.prompt)
+        tb = next(b for b in self.PF_BUCKETS if L <= b)
+        st = self._pf_state(tb)
+        h = st["host"]
+        h.zero_()
+        h[0:L] = torch.tensor(s.prompt, dtype=torch.int32)
+        h[tb:tb + L] = torch.arange(L, dtype=torch.int32)
+        h[2 * tb:3 * tb] = -1
+        h[2 * tb:2 * tb + L] = torch.tensor([s.pages[p // PAGE] * PAGE + p % PAGE for p in range(L)], dtype=torch.int32)
+        h[3 * tb + 0], h[3 * tb + 1], h[3 * tb + 2], h[3 * tb + 3] = L, L, s.slot, L - 1
+        self.h2d_bytes += h.numel() * 4
+        with torch.cuda.stream(self.stream):
+            st["stage"].copy_(h, non_blocking=True)
+            st["graph"].replay()
+        self.kernel_launches += self.launches_per_decode_step()
 
     def _prefill_chunk(self, chunk) -> None:
         dev, i32 = self.device, torch.int32

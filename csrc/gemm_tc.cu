@@ -191,25 +191,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
           wait_flag_ge(p.wait_flag, target);
         }
-        // one warp per token: sum of squares of the raw input row (bf16 -> fp32)
-        for (int t = warp - 2; t < BN; t += 4) {
-          const int tok = tok0 + t;
-          float ss = 0.f;
-          if (tok < p.m_tok) {
-            const uint4* row = reinterpret_cast<const uint4*>(p.norm_src + static_cast<size_t>(tok) * p.k);
-            for (int i = lane; i < p.k / 8; i += 32) {
-              uint4 v = row[i];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        // one warp per token, FOUR tokens in flight per warp (the loop is L2-latency bound: a row is
+        // 16 x 128-bit loads per lane, the next row's loads must not wait for this row's reduction)
+        const int kv8 = p.k / 8;
+        for (int t = warp - 2; t < BN; t += 16) {
+          float ss[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint4* rowp[4];
+          bool live[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int tok = tok0 + t + 4 * u;
+            live[u] = (t + 4 * u < BN) && tok < p.m_tok;
+            rowp[u] = reinterpret_cast<const uint4*>(p.norm_src + static_cast<size_t>(live[u] ? tok : tok0) * p.k);
+          }
+          for (int i = lane; i < kv8; i += 32) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = live[u] ? rowp[u][i] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float2 f = __bfloat1622float2(h[j]);
-                ss += f.x * f.x + f.y * f.y;
+                ss[u] += f.x * f.x + f.y * f.y;
               }
             }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          if (lane == 0) rstd_s[t] = (tok < p.m_tok) ? rsqrtf(ss / static_cast<float>(p.k) + p.eps) : 0.f;
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+            if (lane == 0 && t + 4 * u < BN)
+              rstd_s[t + 4 * u] = live[u] ? rsqrtf(ss[u] / static_cast<float>(p.k) + p.eps) : 0.f;
+          }
         }
       } else {
         for (int t = et; t < BN; t += 128) {

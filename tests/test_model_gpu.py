@@ -115,3 +115,26 @@ def test_piece_fp8_close_to_oracle(name):
                 cos = torch.nn.functional.cosine_similarity(got[b].float(), ref.float(), dim=0).item()
                 assert cos > 0.98, cos
     runner.close()
+
+
+def test_graph_prefill_matches_eager_prefill():
+    """Single short prompts take the CUDA-graph prefill path (TTFT); results equal the eager chunked path."""
+    cfg = resolve_config("tiny-llama")
+    outs = []
+    for graphs in (True, False):
+        r = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=4, groups=1, max_seq_len=256,
+                      max_prefill_tokens=128, seed=0, use_graphs=graphs)
+        toks = []
+        for slot, L in enumerate((5, 16, 17, 40)):
+            s = SeqInit(slot=slot, prompt=[(3 * i + slot) % cfg.vocab_size for i in range(L)], pages=[1 + 2 * slot, 2 + 2 * slot],
+                        temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=slot)
+            r.prefill([s])
+            toks.append(int(r.tokens[slot]))
+        if graphs:
+            assert set(r._pf) == {16, 32, 64}
+        r.decode(4)
+        r.sync()
+        hist, hp = r.read_history()
+        outs.append((toks, hist[:4, :5].tolist(), hp[:4].tolist()))
+        r.close()
+    assert outs[0] == outs[1]
