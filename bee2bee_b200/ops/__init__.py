@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import importlib
 import importlib.util
+import os
 from typing import Optional
 
 import torch
@@ -88,6 +89,9 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
+#: use the persistent stream-K kernel for token tiles <= 64 (decode); False = cluster split-K kernel
+STREAMK = os.environ.get("B2B_STREAMK", "1") != "0"
+
 #: (n_out, k) -> split-K override (tuning / sweeps)
 SPLITK_OVERRIDE = {}
 
@@ -123,7 +127,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
-         dbg: int = 0, w_scale: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+         dbg: int = 0, w_scale: Optional[torch.Tensor] = None, streamk: Optional[bool] = None) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -145,7 +149,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag, dbg, w_scale)
+                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk)
     return out
 
 

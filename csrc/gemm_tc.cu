@@ -454,6 +454,11 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   return 0;
 }
 
+int make_tmap_shared(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     int elt_bytes) {
+  return make_tmap(m, ptr, rows, cols, ld, box_rows, elt_bytes);
+}
+
 template <int BN, int EPI, bool FP8>
 static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;

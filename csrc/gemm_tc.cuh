@@ -71,5 +71,8 @@ struct GemmParams {
 
 // Host launcher (gemm_tc.cu). Returns cudaError_t as int.
 int launch_gemm_tc(const GemmParams& p, const void* w, const void* x, int bn, cudaStream_t stream);
+// Persistent stream-K variant (gemm_sk.cu), bn <= 64. Returns -5 when the problem does not fit its workspace.
+int launch_gemm_sk(const GemmParams& p, const void* w, const void* x, int bn, cudaStream_t stream);
+int gemm_sk_init();
 
 }  // namespace b2b
