@@ -268,6 +268,27 @@ __global__ void __launch_bounds__(192, 1) gemm_sk_kernel(const __grid_constant__
         cur_tok_tile = tok_tile;
       }
 
+      // Owner of a tile that other CTAs contributed to: their partials were produced at the START of
+      // those CTAs' ranges, i.e. long ago -- fetch and sum them into registers now, while this CTA's
+      // own MMAs for the tile are still running, so the L2 round trips are off the critical path.
+      float pacc[BN];
+      int parts = 0;
+      if (owner && !full) {
+        const int last_cta = static_cast<int>((static_cast<long long>(sg.tile + 1) * sk.nkb - 1) / sk.ipc);
+        parts = last_cta - cta;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(&sk.counters[sg.tile]) < static_cast<uint32_t>(parts)) {
+          if (++spins > B2B_SPIN_LIMIT) { __trap(); }
+        }
+        const float* wbase = sk.ws + static_cast<size_t>(sg.tile) * sk.max_parts * BN * SK_BM + row;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) pacc[c] = 0.f;
+        for (int r = 0; r < parts; ++r) {
+#pragma unroll
+          for (int c = 0; c < BN; ++c) pacc[c] += __ldcg(wbase + (static_cast<size_t>(r) * BN + c) * SK_BM);
+        }
+      }
+
       mbar_wait(&tfull_bar[acc], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
@@ -291,43 +312,35 @@ __global__ void __launch_bounds__(192, 1) gemm_sk_kernel(const __grid_constant__
         sk_epi_bar();
         if (et == 0) atomicAdd(&sk.counters[sg.tile], 1u);
       } else {
-        int parts = 0;
-        if (!full) {
-          const int last_cta = static_cast<int>((static_cast<long long>(sg.tile + 1) * sk.nkb - 1) / sk.ipc);
-          parts = last_cta - cta;
-          uint32_t spins = 0;
-          while (ld_acquire_gpu(&sk.counters[sg.tile]) < static_cast<uint32_t>(parts)) {
-            if (++spins > B2B_SPIN_LIMIT) { __trap(); }
-          }
-        }
         const EpiCtx ectx = epi_setup<EPI, FP8>(p, tile_n, row);
         if (p.free_flag != nullptr)
           wait_flag_ge(p.free_flag, *reinterpret_cast<const volatile uint32_t*>(p.signal_epoch));
-        const float* wbase = sk.ws + static_cast<size_t>(sg.tile) * sk.max_parts * BN * SK_BM + row;
         if constexpr (EPI == EPI_GLU) {
           if (row >= 64) {
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < BN; c += 16) {
               float v[16];
               tmem_ld16(taddr + c, v);
-              for (int r = 0; r < parts; ++r)
+              if (parts > 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldcg(wbase + (static_cast<size_t>(r) * BN + c + i) * SK_BM);
+                for (int i = 0; i < 16; ++i) v[i] += pacc[c + i];
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) xch[(c + i) * 64 + (row - 64)] = v[i];
             }
           }
           sk_epi_bar();
         }
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BN; c += 16) {
           if (EPI == EPI_GLU && row >= 64) break;
           if (tok0 + c >= p.m_tok) break;
           float v[16];
           tmem_ld16(taddr + c, v);
-          for (int r = 0; r < parts; ++r)
+          if (parts > 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldcg(wbase + (static_cast<size_t>(r) * BN + c + i) * SK_BM);
+            for (int i = 0; i < 16; ++i) v[i] += pacc[c + i];
+          }
           epi_apply16<EPI, FP8>(p, ectx, v, c, tok0, tile_n, row, lane, rstd_s, xch);
         }
         tc_fence_before();

@@ -57,7 +57,10 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   pdl_wait();
   __shared__ float red_f[32];
   __shared__ int red_i[32];
-  __shared__ float hist[NBINS];
+  __shared__ uint32_t hist_lo[NBINS];     // 32.32 fixed-point mass per bin: native 32-bit ATOMS.ADD on the
+  __shared__ uint32_t hist_hi[NBINS];     // low word, carries (rare) bump the high word
+  __shared__ unsigned long long red_u[32];
+  __shared__ unsigned long long s_u[2];
   __shared__ float s_bcast[4];
   __shared__ int s_ib[4];
 
@@ -102,38 +105,49 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   int token = s_ib[0];
 
   if (!greedy) {
+    // Histograms accumulate probability mass in 32.32 fixed point with NATIVE 64-bit shared-memory
+    // atomics: a float atomicAdd on shared memory is a CAS loop (ATOMS.CAST) that collapses when most
+    // tokens land in a few bins (313 us for 32 x 128k logits, profiles/launches_decode_step.md).
+    auto fx = [](float e) { return static_cast<uint32_t>(fminf(e * 4294967296.0f, 4294967040.0f)); };
+    auto hist_add = [&](int bin, uint32_t f) {
+      const uint32_t old = atomicAdd(&hist_lo[bin], f);
+      if (old + f < old) atomicAdd(&hist_hi[bin], 1u);
+    };
+    auto hist_get = [&](int bin) { return (static_cast<unsigned long long>(hist_hi[bin]) << 32) | hist_lo[bin]; };
     // ---- pass 2: level-1 histogram of unnormalised probs e = exp(l - max) in (0, 1]
     // key = top 12 bits below the sign of the float bits (monotone in e)
-    for (int i = tid; i < NBINS; i += SAMP_THREADS) hist[i] = 0.f;
+    for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
     __syncthreads();
-    float zsum = 0.f;
+    unsigned long long zsum = 0ull;
     for (int i = tid; i < V; i += SAMP_THREADS) {
       const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
-      zsum += e;
-      atomicAdd(&hist[__float_as_uint(e) >> 19], e);
+      const uint32_t f = fx(e);
+      zsum += f;
+      hist_add(__float_as_uint(e) >> 19, f);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
-    if (lane == 0) red_f[warp] = zsum;
+    if (lane == 0) red_u[warp] = zsum;
     __syncthreads();
     if (warp == 0) {
-      float z = red_f[lane];
+      unsigned long long z = red_u[lane];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-      if (lane == 0) s_bcast[1] = z;
+      if (lane == 0) s_u[0] = z;
     }
     __syncthreads();
-    const float Z = s_bcast[1];
-    const float need = top_p * Z;          // mass that must be covered by the kept set
+    const unsigned long long Z = s_u[0];
+    const unsigned long long need = static_cast<unsigned long long>(static_cast<double>(top_p) * static_cast<double>(Z));
 
-    // find boundary bin: largest bin index B1 with sum_{bin >= B1} >= need  (warp 0 scans from the top)
+    // boundary bin: largest bin index B1 with sum_{bin >= B1} >= need  (warp 0 scans from the top)
     if (warp == 0) {
-      float carry = 0.f; int found = -1; float above = 0.f;
+      unsigned long long carry = 0ull, above = 0ull;
+      int found = -1;
       for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
-        const float v = hist[base + (31 - lane)];     // lane 0 = highest bin of the chunk
-        float pre = v;
+        const unsigned long long v = hist_get(base + (31 - lane));     // lane 0 = highest bin of the chunk
+        unsigned long long pre = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
         const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
         if (ball) {
           const int l0 = __ffs(ball) - 1;
@@ -143,28 +157,29 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
           carry += __shfl_sync(0xffffffffu, pre, 31);
         }
       }
-      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_bcast[2] = above; }
+      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_u[1] = above; }
     }
     __syncthreads();
     const int B1 = s_ib[1];
-    const float above1 = s_bcast[2];       // mass strictly above the boundary bin
+    const unsigned long long above1 = s_u[1];       // mass strictly above the boundary bin
 
     // ---- pass 3: level-2 histogram inside the boundary bin (next 12 bits)
-    for (int i = tid; i < NBINS; i += SAMP_THREADS) hist[i] = 0.f;
+    for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
     __syncthreads();
     for (int i = tid; i < V; i += SAMP_THREADS) {
       const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
       const uint32_t u = __float_as_uint(e);
-      if (static_cast<int>(u >> 19) == B1) atomicAdd(&hist[(u >> 7) & (NBINS - 1)], e);
+      if (static_cast<int>(u >> 19) == B1) hist_add((u >> 7) & (NBINS - 1), fx(e));
     }
     __syncthreads();
     if (warp == 0) {
-      float carry = above1; int found = -1; float kept = 0.f;
+      unsigned long long carry = above1, kept = 0ull;
+      int found = -1;
       for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
-        const float v = hist[base + (31 - lane)];
-        float pre = v;
+        const unsigned long long v = hist_get(base + (31 - lane));
+        unsigned long long pre = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
         const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
         if (ball) {
           const int l0 = __ffs(ball) - 1;
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
         }
       }
       if (found < 0) { found = 0; kept = carry; }
-      if (lane == 0) { s_ib[2] = found; s_bcast[3] = kept; }
+      if (lane == 0) { s_ib[2] = found; s_bcast[3] = static_cast<float>(static_cast<double>(kept) * (1.0 / 4294967296.0)); }
     }
     __syncthreads();
     const uint32_t thr_bits = (static_cast<uint32_t>(B1) << 19) | (static_cast<uint32_t>(s_ib[2]) << 7);
