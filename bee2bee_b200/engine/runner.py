@@ -194,33 +194,29 @@ class GpuRunner:
         if st is not None:
             return st
         dev, i32 = self.device, torch.int32
-        n = 3 * tb + 8
+        mp = self.max_pages_per_seq
+        n = 3 * tb + 8 + mp
         host = torch.zeros(n, dtype=i32).pin_memory()
         stage = torch.zeros(n, device=dev, dtype=i32)
         ids, pos, slots = stage[0:tb], stage[tb:2 * tb], stage[2 * tb:3 * tb]
         qlen, kvlen, row32, last32 = (stage[3 * tb + i:3 * tb + i + 1] for i in range(4))
+        bt = stage[3 * tb + 8:3 * tb + 8 + mp].view(1, mp)              # this sequence's block-table row
         qstart = torch.zeros(1, device=dev, dtype=i32)
-        tok_tmp = torch.zeros(1, device=dev, dtype=i32)
+        last64 = torch.zeros(1, device=dev, dtype=torch.int64)
         st = {"host": host, "stage": stage, "graph": None}
 
         def body():
-            row = row32.long()
+            # no torch gather/scatter ops in here: every per-sequence input is either staged by the single
+            # H2D copy or addressed through the device-side row offset `row32`
+            last64.copy_(last32)
             meta = BatchMeta(ids=ids, positions=pos, slots=slots, q_start=qstart, q_len=qlen, kv_len=kvlen,
-                             block_table=self.block_table.index_select(0, row), n_tokens=tb, n_seqs=1, max_q=tb,
-                             last_idx=last32.long())
+                             block_table=bt, n_tokens=tb, n_seqs=1, max_q=tb, last_idx=last64)
             out = self.piece.forward(meta)
-            sel = lambda x: x.index_select(0, row)
-            seen_sel = sel(self.seen)
-            ops.sample(out, tok_tmp, seen=seen_sel, temperature=sel(self.temperature), top_p=sel(self.top_p),
-                       rep_penalty=sel(self.rep_pen), seeds=sel(self.seeds), step=self.step_ctr,
-                       vocab=self.cfg.vocab_size, softcap=self.cfg.final_softcap)
-            self.seen.index_copy_(0, row, seen_sel)
-            self.tokens.index_copy_(0, row, tok_tmp)
-            self.history[:, 0].index_copy_(0, row, tok_tmp)
-            self.hist_pos.index_fill_(0, row, 1)
-            self.positions.index_copy_(0, row, kvlen - 1)
-            self.kv_len.index_copy_(0, row, kvlen)
-            self.q_len.index_fill_(0, row, 1)
+            ops.sample(out, self.tokens, seen=self.seen, temperature=self.temperature, top_p=self.top_p,
+                       rep_penalty=self.rep_pen, seeds=self.seeds, step=self.step_ctr, vocab=self.cfg.vocab_size,
+                       softcap=self.cfg.final_softcap, history=self.history.data_ptr(), hist_pos=self.hist_pos,
+                       hist_stride=self.hist_len, row_base=row32.data_ptr())
+            ops.native().set_decode_state(self.positions, self.kv_len, self.q_len, row32.data_ptr(), kvlen.data_ptr())
 
         saved = (self.seen.clone(), self.tokens.clone(), self.history[:, 0].clone(), self.hist_pos.clone(),
                  self.positions.clone(), self.kv_len.clone(), self.q_len.clone(), self.step_ctr.clone())
@@ -252,6 +248,7 @@ class GpuRunner:
         h[2 * tb:3 * tb] = -1
         h[2 * tb:2 * tb + L] = torch.tensor([s.pages[p // PAGE] * PAGE + p % PAGE for p in range(L)], dtype=torch.int32)
         h[3 * tb + 0], h[3 * tb + 1], h[3 * tb + 2], h[3 * tb + 3] = L, L, s.slot, L - 1
+        h[3 * tb + 8:3 * tb + 8 + len(s.pages)] = torch.tensor(s.pages, dtype=torch.int32)
         self.h2d_bytes += h.numel() * 4
         with torch.cuda.stream(self.stream):
             st["stage"].copy_(h, non_blocking=True)

@@ -223,10 +223,10 @@ def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, 
 # ---------------------------------------------------------------------- sampler
 def sample(logits, out_tokens, *, seen=None, temperature=None, top_p=None, rep_penalty=None, seeds=None, step=None,
            peer_tokens=0, history=0, hist_pos=None, hist_stride=0, signal_flag=0, signal_epoch=0, done_counter=0,
-           vocab=0, softcap=0.0):
+           vocab=0, softcap=0.0, row_base=0):
     native().sample(logits, seen, out_tokens, peer_tokens, history, hist_pos, hist_stride, vocab, softcap,
                     temperature, top_p,
-                    rep_penalty, seeds, step, signal_flag, signal_epoch, done_counter)
+                    rep_penalty, seeds, step, signal_flag, signal_epoch, done_counter, row_base)
     return out_tokens
 
 

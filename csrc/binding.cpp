@@ -244,7 +244,7 @@ void sample(const Tensor& logits, const OptT& seen, const Tensor& out_tokens, in
             int64_t history, const OptT& hist_pos, int64_t hist_stride, int64_t vocab, double softcap,
             const OptT& temperature, const OptT& top_p,
             const OptT& rep_penalty, const OptT& seeds, const OptT& step, int64_t signal_flag, int64_t signal_epoch,
-            int64_t done_counter) {
+            int64_t done_counter, int64_t row_base) {
   TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.stride(1) == 1, "logits: fp32");
   c10::cuda::CUDAGuard guard(logits.device());
   int* hp = ptr_or_null<int>(hist_pos);
@@ -256,8 +256,17 @@ void sample(const Tensor& logits, const OptT& seen, const Tensor& out_tokens, in
                            ptr_or_null<const float>(temperature), ptr_or_null<const float>(top_p),
                            ptr_or_null<const float>(rep_penalty), ptr_or_null<const uint32_t>(seeds),
                            ptr_or_null<const uint32_t>(step), as_ptr<uint32_t>(signal_flag),
-                           as_ptr<uint32_t>(signal_epoch), as_ptr<uint32_t>(done_counter), cur_stream()),
+                           as_ptr<uint32_t>(signal_epoch), as_ptr<uint32_t>(done_counter), as_ptr<const int>(row_base),
+                           cur_stream()),
         "sample");
+}
+
+void set_decode_state(const Tensor& positions, const Tensor& kv_len, const Tensor& q_len, int64_t row, int64_t kvlen) {
+  c10::cuda::CUDAGuard guard(positions.device());
+  check(b2b::launch_set_decode_state(reinterpret_cast<int*>(positions.data_ptr()), reinterpret_cast<int*>(kv_len.data_ptr()),
+                                     reinterpret_cast<int*>(q_len.data_ptr()), as_ptr<const int>(row),
+                                     as_ptr<const int>(kvlen), cur_stream()),
+        "set_decode_state");
 }
 
 void mark_seen(const Tensor& ids, const Tensor& seq_of, const Tensor& seen, int64_t vocab) {
@@ -336,6 +345,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention", &attention);
   m.def("sample", &sample);
   m.def("mark_seen", &mark_seen);
+  m.def("set_decode_state", &set_decode_state);
   m.def("peer_alloc", &peer_alloc);
   m.def("peer_free", &peer_free);
   m.def("ipc_export", &ipc_export);

@@ -264,7 +264,21 @@ __global__ void decode_advance_kernel(int* positions, int* kv_len, int* slots, c
   slots[i] = (pg < max_pages) ? block_table[static_cast<size_t>(i) * max_pages + pg] * 64 + (pos % 64) : -1;
 }
 
+// After a (graph-captured) prefill: install the decode state of the sequence in batch row *row.
+__global__ void set_decode_state_kernel(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = row[0], n = kvlen[0];
+  positions[b] = n - 1;
+  kv_len[b] = n;
+  q_len[b] = 1;
+}
+
 // ------------------------------------------------------------------ launchers
+int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen, cudaStream_t s) {
+  launch_kernel(set_decode_state_kernel, dim3(1), dim3(1), 0, s, 1, positions, kv_len, q_len, row, kvlen);
+  return static_cast<int>(cudaGetLastError());
+}
 int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
                           int max_pages, int n, cudaStream_t s) {
   launch_kernel(decode_advance_kernel, dim3((n + 127) / 128), dim3(128), 0, s, 1, positions, kv_len, slots, q_len, block_table, max_pages, n);

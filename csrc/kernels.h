@@ -37,7 +37,8 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
                   const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
                   const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
                   const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
-                  cudaStream_t s);
+                  const int* row_base, cudaStream_t s);
+int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen, cudaStream_t s);
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s);
 
 // gemm_tc.cu

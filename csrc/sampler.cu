@@ -50,6 +50,7 @@ struct SampleParams {
   uint32_t* signal_flag;    // peer flag (token handoff) or null
   uint32_t* signal_epoch;   // local epoch for the flag
   uint32_t* done_counter;   // local, self-resetting
+  const int* row_base;      // optional: per-sequence state (seen/params/tokens/history) lives at row *row_base + b
 };
 
 __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams p) {
@@ -65,13 +66,14 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   __shared__ int s_ib[4];
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bb = (p.row_base != nullptr ? p.row_base[0] : 0) + b;     // row of the per-sequence state
   const int V = p.vocab;
   const float* logits = p.logits + static_cast<size_t>(b) * p.ld;
   const float cap = p.softcap;
-  uint32_t* seen = p.seen ? p.seen + static_cast<size_t>(b) * ((V + 31) / 32) : nullptr;
-  const float temp = p.temperature ? p.temperature[b] : 0.f;
-  const float pen = p.rep_penalty ? p.rep_penalty[b] : 1.f;
-  const float top_p = p.top_p ? p.top_p[b] : 1.f;
+  uint32_t* seen = p.seen ? p.seen + static_cast<size_t>(bb) * ((V + 31) / 32) : nullptr;
+  const float temp = p.temperature ? p.temperature[bb] : 0.f;
+  const float pen = p.rep_penalty ? p.rep_penalty[bb] : 1.f;
+  const float top_p = p.top_p ? p.top_p[bb] : 1.f;
   const bool greedy = !(temp > 0.f);
   const float inv_temp = greedy ? 1.f : 1.f / temp;
   const uint32_t* seen_r = (pen != 1.f) ? seen : nullptr;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
 
     // ---- pass 4: multinomial draw over the kept set, in index order
     const uint32_t stepv = p.step ? *p.step : 0u;
-    const uint32_t h = hash_u32((p.seeds ? p.seeds[b] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
+    const uint32_t h = hash_u32((p.seeds ? p.seeds[bb] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
     const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float target = u01 * kept_mass;
     // one contiguous chunk per WARP, lanes stride by one element -> fully coalesced reads
@@ -253,14 +255,14 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   }
 
   if (tid == 0) {
-    p.out_tokens[b] = token;
+    p.out_tokens[bb] = token;
     if (seen != nullptr) atomicOr(&seen[token >> 5], 1u << (token & 31));
     if (p.history != nullptr) {
-      const int pos = p.hist_pos[b];
-      if (pos < p.hist_stride) p.history[static_cast<size_t>(b) * p.hist_stride + pos] = token;
-      p.hist_pos_out[b] = pos + 1;
+      const int pos = p.hist_pos[bb];
+      if (pos < p.hist_stride) p.history[static_cast<size_t>(bb) * p.hist_stride + pos] = token;
+      p.hist_pos_out[bb] = pos + 1;
     }
-    if (p.peer_tokens != nullptr && p.peer_tokens != p.out_tokens) p.peer_tokens[b] = token;
+    if (p.peer_tokens != nullptr && p.peer_tokens != p.out_tokens) p.peer_tokens[bb] = token;
     if (p.signal_flag != nullptr) {
       __threadfence_system();
       const uint32_t prev = atomicAdd(p.done_counter, 1u);
@@ -290,12 +292,12 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
                   const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
                   const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
                   const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
-                  cudaStream_t s) {
+                  const int* row_base, cudaStream_t s) {
   SampleParams p;
   p.logits = logits; p.seen = seen; p.out_tokens = out_tokens; p.peer_tokens = peer_tokens; p.history = history;
   p.hist_pos = hist_pos; p.hist_pos_out = hist_pos_out; p.hist_stride = hist_stride; p.vocab = vocab; p.ld = ld; p.softcap = softcap;
   p.temperature = temperature; p.top_p = top_p; p.rep_penalty = rep_penalty; p.seeds = seeds; p.step = step;
-  p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter;
+  p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter; p.row_base = row_base;
   return static_cast<int>(launch_kernel(sample_kernel, dim3(batch), dim3(SAMP_THREADS), 0, s, 1, p));
 }
 
