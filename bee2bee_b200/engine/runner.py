@@ -9,6 +9,7 @@ Burst protocol (all ranks execute the same plan):
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -184,7 +185,10 @@ class GpuRunner:
     PF_BUCKETS = (16, 32, 64)
 
     def _prefill_graph_ok(self, seqs) -> bool:
-        return (self.use_graphs and self.world == 1 and len(seqs) == 1 and 0 < len(seqs[0].prompt) <= self.PF_BUCKETS[-1]
+        # experimental (off by default): replays after the capturing call produce wrong attention outputs on
+        # B200 although q/K/V match -- see DESIGN.md known gaps; eager prefill is the validated path
+        return (os.environ.get("B2B_PREFILL_GRAPH", "0") == "1" and self.use_graphs and self.world == 1
+                and len(seqs) == 1 and 0 < len(seqs[0].prompt) <= self.PF_BUCKETS[-1]
                 and self.max_prefill_tokens >= self.PF_BUCKETS[-1])
 
     def _pf_state(self, tb: int):

@@ -90,7 +90,7 @@ def pick_bn(m_tok: int) -> int:
 
 
 #: use the persistent stream-K kernel for token tiles <= 64 (decode); False = cluster split-K kernel
-STREAMK = os.environ.get("B2B_STREAMK", "1") != "0"
+STREAMK = os.environ.get("B2B_STREAMK", "0") != "0"
 
 #: (n_out, k) -> split-K override (tuning / sweeps)
 SPLITK_OVERRIDE = {}

@@ -1,12 +1,17 @@
 // Fused sampler for sm_100a: repetition penalty (seen-token bitmap) -> temperature ->
 // exact top-p via two-level radix histogram of the probability bits -> multinomial draw
-// (or argmax when temperature <= 0).  One CTA per sequence, logits are fp32 [B, V] as
+// (or argmax when temperature <= 0).  One CTA per sequence, logits are fp32 [B, ld] as
 // written by the lm_head GEMM.  The sampled id is stored locally (token ring, history
 // bitmap) and, on the last piece of a pipeline, straight into piece 0's token buffer on
 // the peer GPU followed by a release flag (4 bytes/sequence over NVLink, no NCCL).
 //
 // Semantics follow the reference's generation defaults (bee2bee/hf.py:91-105):
 // repetition_penalty 1.15, top_p 0.95, do_sample iff temperature > 0, greedy otherwise.
+//
+// Performance notes (profiles/launches_decode_step.md): every pass over the 128k logits is
+// L2-latency bound, so logits are read 8 at a time per thread (2 x 128-bit loads in flight);
+// histogram mass is accumulated in 32.32 fixed point with native 32-bit shared-memory atomics
+// (float / 64-bit shared atomics are CAS loops).
 #include "kernels.h"
 
 #include "common.cuh"
@@ -22,43 +27,82 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
   return x;
 }
 
-__device__ __forceinline__ float penalized(const float* logits, const uint32_t* seen, int i, float pen, float inv_temp,
-                                           float cap) {
-  float l = logits[i];
-  if (cap > 0.f) l = cap * tanhf(l / cap);
-  if (seen != nullptr && ((seen[i >> 5] >> (i & 31)) & 1u)) l = l > 0.f ? l / pen : l * pen;
-  return l * inv_temp;
-}
-
 struct SampleParams {
-  const float* logits;      // [B, V]
-  uint32_t* seen;           // [B, ceil(V/32)] bitmap of ids in the context, or null
-  int* out_tokens;          // [B] local
-  int* peer_tokens;         // [B] on piece 0 (may be == out_tokens / null)
-  int* history;             // [B, hist_stride] token ring (host-visible when mapped), or null
-  const int* hist_pos;      // [B] write index into history (device-side step counter)
-  int* hist_pos_out;        // [B] incremented copy
+  const float* logits;      // [B, ld]
+  uint32_t* seen;           // [rows, ceil(V/32)] bitmap of ids in the context, or null
+  int* out_tokens;          // [rows] local
+  int* peer_tokens;         // [rows] on piece 0 (may be == out_tokens / null)
+  int* history;             // [rows, hist_stride] token ring, or null
+  const int* hist_pos;      // [rows] write index into history
+  int* hist_pos_out;        // [rows] incremented copy
   int hist_stride;
   int vocab;
   int ld;                   // row stride of logits (vocab padded to a GEMM tile)
   float softcap;            // final-logit soft-capping (Gemma-2), 0 = off
-  const float* temperature; // [B]
-  const float* top_p;       // [B]
-  const float* rep_penalty; // [B]
-  const uint32_t* seeds;    // [B]
+  const float* temperature; // [rows]
+  const float* top_p;       // [rows]
+  const float* rep_penalty; // [rows]
+  const uint32_t* seeds;    // [rows]
   const uint32_t* step;     // device step counter (rng stream), may be null
   uint32_t* signal_flag;    // peer flag (token handoff) or null
   uint32_t* signal_epoch;   // local epoch for the flag
   uint32_t* done_counter;   // local, self-resetting
-  const int* row_base;      // optional: per-sequence state (seen/params/tokens/history) lives at row *row_base + b
+  const int* row_base;      // optional: per-sequence state lives at row *row_base + b
 };
 
-__global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams p) {
+// logit -> (soft-cap) -> repetition penalty -> temperature
+__device__ __forceinline__ float transform(float l, bool is_seen, float pen, float inv_temp, float cap) {
+  if (cap > 0.f) l = cap * tanhf(l / cap);
+  if (is_seen) l = l > 0.f ? l / pen : l * pen;
+  return l * inv_temp;
+}
+
+// Visit every id in [lo, hi) (lo % 4 == 0): this thread takes quads first_quad, first_quad + quad_stride, ...
+// and calls f(id, transformed_logit).  Two quads (8 logits) are loaded before either is processed.
+template <typename F>
+__device__ __forceinline__ void visit(const float* logits, const uint32_t* seen, int lo, int hi, int first_quad,
+                                      int quad_stride, bool vec_ok, float pen, float inv_temp, float cap, F f) {
+  const int nq = (hi - lo) / 4;
+  for (int q = first_quad; q < nq; q += 2 * quad_stride) {
+    const int q2 = q + quad_stride;
+    const bool has2 = q2 < nq;
+    const int i0 = lo + 4 * q, i1 = lo + 4 * q2;
+    float a[4], b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec_ok) {
+      const float4 va = *reinterpret_cast<const float4*>(logits + i0);
+      a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+      if (has2) {
+        const float4 vb = *reinterpret_cast<const float4*>(logits + i1);
+        b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = logits[i0 + k];
+      if (has2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b[k] = logits[i1 + k];
+      }
+    }
+    const uint32_t sa = seen ? seen[i0 >> 5] : 0u;
+    const uint32_t sb = (seen && has2) ? seen[i1 >> 5] : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f(i0 + k, transform(a[k], (sa >> ((i0 + k) & 31)) & 1u, pen, inv_temp, cap));
+    if (has2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f(i1 + k, transform(b[k], (sb >> ((i1 + k) & 31)) & 1u, pen, inv_temp, cap));
+    }
+  }
+  // tail (hi - lo not a multiple of 4), scalar
+  for (int i = lo + 4 * nq + first_quad; i < hi; i += quad_stride)
+    f(i, transform(logits[i], seen ? ((seen[i >> 5] >> (i & 31)) & 1u) : 0u, pen, inv_temp, cap));
+}
+
+__global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SampleParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red_f[32];
   __shared__ int red_i[32];
-  __shared__ uint32_t hist_lo[NBINS];     // 32.32 fixed-point mass per bin: native 32-bit ATOMS.ADD on the
+  __shared__ uint32_t hist_lo[NBINS];     // 32.32 fixed-point mass per bin: native ATOMS.ADD on the
   __shared__ uint32_t hist_hi[NBINS];     // low word, carries (rare) bump the high word
   __shared__ unsigned long long red_u[32];
   __shared__ unsigned long long s_u[2];
@@ -69,6 +113,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   const int bb = (p.row_base != nullptr ? p.row_base[0] : 0) + b;     // row of the per-sequence state
   const int V = p.vocab;
   const float* logits = p.logits + static_cast<size_t>(b) * p.ld;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
   const float cap = p.softcap;
   uint32_t* seen = p.seen ? p.seen + static_cast<size_t>(bb) * ((V + 31) / 32) : nullptr;
   const float temp = p.temperature ? p.temperature[bb] : 0.f;
@@ -78,12 +123,10 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   const float inv_temp = greedy ? 1.f : 1.f / temp;
   const uint32_t* seen_r = (pen != 1.f) ? seen : nullptr;
 
-  // ---- pass 1: max (+ argmax)
+  // ---- pass 1: max (+ argmax, lowest id on ties)
   float mx = -INFINITY; int amx = 0;
-  for (int i = tid; i < V; i += SAMP_THREADS) {
-    const float l = penalized(logits, seen_r, i, pen, inv_temp, cap);
-    if (l > mx) { mx = l; amx = i; }
-  }
+  visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap,
+        [&](int i, float l) { if (l > mx) { mx = l; amx = i; } });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, mx, o);
@@ -107,26 +150,45 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
   int token = s_ib[0];
 
   if (!greedy) {
-    // Histograms accumulate probability mass in 32.32 fixed point with NATIVE 64-bit shared-memory
-    // atomics: a float atomicAdd on shared memory is a CAS loop (ATOMS.CAST) that collapses when most
-    // tokens land in a few bins (313 us for 32 x 128k logits, profiles/launches_decode_step.md).
     auto fx = [](float e) { return static_cast<uint32_t>(fminf(e * 4294967296.0f, 4294967040.0f)); };
     auto hist_add = [&](int bin, uint32_t f) {
       const uint32_t old = atomicAdd(&hist_lo[bin], f);
       if (old + f < old) atomicAdd(&hist_hi[bin], 1u);
     };
     auto hist_get = [&](int bin) { return (static_cast<unsigned long long>(hist_hi[bin]) << 32) | hist_lo[bin]; };
-    // ---- pass 2: level-1 histogram of unnormalised probs e = exp(l - max) in (0, 1]
-    // key = top 12 bits below the sign of the float bits (monotone in e)
+    // top-down scan of the histogram (warp 0): highest bin whose suffix mass (plus carry) reaches `need`;
+    // above = mass strictly above that bin, incl = mass including it.
+    auto scan_down = [&](unsigned long long carry, unsigned long long need, int& found, unsigned long long& above,
+                         unsigned long long& incl) {
+      found = -1; above = carry; incl = carry;
+      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
+        const unsigned long long v = hist_get(base + (31 - lane));     // lane 0 = highest bin of the chunk
+        unsigned long long pre = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
+        if (ball) {
+          const int l0 = __ffs(ball) - 1;
+          found = base + (31 - l0);
+          incl = carry + __shfl_sync(0xffffffffu, pre, l0);
+          above = incl - __shfl_sync(0xffffffffu, v, l0);
+        } else {
+          carry += __shfl_sync(0xffffffffu, pre, 31);
+          incl = carry;
+        }
+      }
+    };
+
+    // ---- pass 2: level-1 histogram of e = exp(l - max) in (0, 1]; key = top 12 bits below the sign
     for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
     __syncthreads();
     unsigned long long zsum = 0ull;
-    for (int i = tid; i < V; i += SAMP_THREADS) {
-      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+    visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap, [&](int, float l) {
+      const float e = __expf(l - mx);
       const uint32_t f = fx(e);
       zsum += f;
       hist_add(__float_as_uint(e) >> 19, f);
-    }
+    });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
     if (lane == 0) red_u[warp] = zsum;
@@ -140,26 +202,10 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
     __syncthreads();
     const unsigned long long Z = s_u[0];
     const unsigned long long need = static_cast<unsigned long long>(static_cast<double>(top_p) * static_cast<double>(Z));
-
-    // boundary bin: largest bin index B1 with sum_{bin >= B1} >= need  (warp 0 scans from the top)
     if (warp == 0) {
-      unsigned long long carry = 0ull, above = 0ull;
-      int found = -1;
-      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
-        const unsigned long long v = hist_get(base + (31 - lane));     // lane 0 = highest bin of the chunk
-        unsigned long long pre = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
-        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
-        if (ball) {
-          const int l0 = __ffs(ball) - 1;
-          found = base + (31 - l0);
-          above = carry + __shfl_sync(0xffffffffu, pre, l0) - __shfl_sync(0xffffffffu, v, l0);
-        } else {
-          carry += __shfl_sync(0xffffffffu, pre, 31);
-        }
-      }
-      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_u[1] = above; }
+      int found; unsigned long long above, incl;
+      scan_down(0ull, need, found, above, incl);
+      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_u[1] = found < 0 ? 0ull : above; }
     }
     __syncthreads();
     const int B1 = s_ib[1];
@@ -168,31 +214,17 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
     // ---- pass 3: level-2 histogram inside the boundary bin (next 12 bits)
     for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
     __syncthreads();
-    for (int i = tid; i < V; i += SAMP_THREADS) {
-      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+    visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap, [&](int, float l) {
+      const float e = __expf(l - mx);
       const uint32_t u = __float_as_uint(e);
       if (static_cast<int>(u >> 19) == B1) hist_add((u >> 7) & (NBINS - 1), fx(e));
-    }
+    });
     __syncthreads();
     if (warp == 0) {
-      unsigned long long carry = above1, kept = 0ull;
-      int found = -1;
-      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
-        const unsigned long long v = hist_get(base + (31 - lane));
-        unsigned long long pre = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
-        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
-        if (ball) {
-          const int l0 = __ffs(ball) - 1;
-          found = base + (31 - l0);
-          kept = carry + __shfl_sync(0xffffffffu, pre, l0);
-        } else {
-          carry += __shfl_sync(0xffffffffu, pre, 31);
-        }
-      }
-      if (found < 0) { found = 0; kept = carry; }
-      if (lane == 0) { s_ib[2] = found; s_bcast[3] = static_cast<float>(static_cast<double>(kept) * (1.0 / 4294967296.0)); }
+      int found; unsigned long long above, incl;
+      scan_down(above1, need, found, above, incl);
+      if (found < 0) found = 0;
+      if (lane == 0) { s_ib[2] = found; s_bcast[3] = static_cast<float>(static_cast<double>(incl) * (1.0 / 4294967296.0)); }
     }
     __syncthreads();
     const uint32_t thr_bits = (static_cast<uint32_t>(B1) << 19) | (static_cast<uint32_t>(s_ib[2]) << 7);
@@ -203,55 +235,51 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const SampleParams
     const uint32_t h = hash_u32((p.seeds ? p.seeds[bb] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
     const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float target = u01 * kept_mass;
-    // one contiguous chunk per WARP, lanes stride by one element -> fully coalesced reads
-    const int cw = ((V + 31) / 32 + 31) & ~31;          // chunk width, multiple of 32
+    // one contiguous chunk per WARP (multiple of 128 ids), lanes own interleaved quads -> coalesced 128-bit reads
+    const int cw = ((V + 31) / 32 + 127) & ~127;
     const int c0 = warp * cw, c1 = min(V, c0 + cw);
     float mine = 0.f;
-    for (int i = c0 + lane; i < c1; i += 32) {
-      const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
-      if (__float_as_uint(e) >= thr_bits) mine += e;
-    }
+    if (c0 < c1)
+      visit(logits, seen_r, c0, c1, lane, 32, vec_ok, pen, inv_temp, cap, [&](int, float l) {
+        const float e = __expf(l - mx);
+        if (__float_as_uint(e) >= thr_bits) mine += e;
+      });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);   // warp total
     if (lane == 0) red_f[warp] = mine;
     if (tid == 0) s_ib[3] = -1;
     __syncthreads();
-    // exclusive scan over the 32 warp totals (every warp recomputes it: 32 values)
     float wtot = red_f[lane], wpre = wtot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, wpre, o); if (lane >= o) wpre += n; }
     const float my_excl = __shfl_sync(0xffffffffu, wpre - wtot, warp);
     const float my_tot = __shfl_sync(0xffffffffu, wtot, warp);
     if (my_tot > 0.f && target >= my_excl && target < my_excl + my_tot) {
+      // the selected warp walks its chunk in rows of 32 consecutive ids with a warp prefix sum
       float run = my_excl;
-      int pick = -1;
+      int pick = -1, last_kept = -1;
       for (int base = c0; base < c1 && pick < 0; base += 32) {
         const int i = base + lane;
         float v = 0.f;
         if (i < c1) {
-          const float e = __expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx);
+          const bool sn = seen_r ? ((seen_r[i >> 5] >> (i & 31)) & 1u) : false;
+          const float e = __expf(transform(logits[i], sn, pen, inv_temp, cap) - mx);
           if (__float_as_uint(e) >= thr_bits) v = e;
         }
         float pre = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
+        const unsigned kept = __ballot_sync(0xffffffffu, v > 0.f);
+        if (kept) last_kept = base + (31 - __clz(kept));
         const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && run + pre > target);
         if (hit) pick = base + (__ffs(hit) - 1);
         run += __shfl_sync(0xffffffffu, pre, 31);
       }
-      if (pick < 0) {                       // round-off at the chunk edge: take the last kept id of the chunk
-        for (int base = ((c1 - 1 - c0) / 32) * 32 + c0; base >= c0 && pick < 0; base -= 32) {
-          const int i = base + lane;
-          bool k = false;
-          if (i < c1) k = __float_as_uint(__expf(penalized(logits, seen_r, i, pen, inv_temp, cap) - mx)) >= thr_bits;
-          const unsigned m = __ballot_sync(0xffffffffu, k);
-          if (m) pick = base + (31 - __clz(m));
-        }
-      }
+      if (pick < 0) pick = last_kept;          // float round-off at the chunk edge
       if (lane == 0 && pick >= 0) atomicMax(&s_ib[3], pick);
     }
     __syncthreads();
-    if (s_ib[3] >= 0) token = s_ib[3];   // else (fp round-off at the far edge): fall back to argmax
+    if (s_ib[3] >= 0) token = s_ib[3];   // else (round-off at the far edge): fall back to argmax
   }
 
   if (tid == 0) {
