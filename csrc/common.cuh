@@ -211,6 +211,17 @@ __device__ __forceinline__ uint32_t mapa_smem(uint32_t local_addr, uint32_t cta_
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
   return r;
 }
+__device__ __forceinline__ void st_dsmem_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_u64(uint32_t cluster_addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint2 ld_dsmem_v2u32(uint32_t cluster_addr) {
+  uint2 v;
+  asm volatile("ld.shared::cluster.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_dsmem_f32(uint32_t cluster_addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }

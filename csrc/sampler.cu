@@ -57,59 +57,59 @@ __device__ __forceinline__ float transform(float l, bool is_seen, float pen, flo
   return l * inv_temp;
 }
 
-// Visit every id in [lo, hi) (lo % 4 == 0): this thread takes quads first_quad, first_quad + quad_stride, ...
-// and calls f(id, transformed_logit).  Two quads (8 logits) are loaded before either is processed.
-template <typename F>
-__device__ __forceinline__ void visit(const float* logits, const uint32_t* seen, int lo, int hi, int first_quad,
-                                      int quad_stride, bool vec_ok, float pen, float inv_temp, float cap, F f) {
-  const int nq = (hi - lo) / 4;
-  for (int q = first_quad; q < nq; q += 2 * quad_stride) {
-    const int q2 = q + quad_stride;
-    const bool has2 = q2 < nq;
-    const int i0 = lo + 4 * q, i1 = lo + 4 * q2;
-    float a[4], b[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec_ok) {
-      const float4 va = *reinterpret_cast<const float4*>(logits + i0);
-      a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-      if (has2) {
-        const float4 vb = *reinterpret_cast<const float4*>(logits + i1);
-        b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) a[k] = logits[i0 + k];
-      if (has2) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) b[k] = logits[i1 + k];
-      }
-    }
-    const uint32_t sa = seen ? seen[i0 >> 5] : 0u;
-    const uint32_t sb = (seen && has2) ? seen[i1 >> 5] : 0u;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f(i0 + k, transform(a[k], (sa >> ((i0 + k) & 31)) & 1u, pen, inv_temp, cap));
-    if (has2) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) f(i1 + k, transform(b[k], (sb >> ((i1 + k) & 31)) & 1u, pen, inv_temp, cap));
-    }
-  }
-  // tail (hi - lo not a multiple of 4), scalar
-  for (int i = lo + 4 * nq + first_quad; i < hi; i += quad_stride)
-    f(i, transform(logits[i], seen ? ((seen[i >> 5] >> (i & 31)) & 1u) : 0u, pen, inv_temp, cap));
+constexpr int SBINS = 2048;          // histogram bins per level (11 + 11 bits of the 28-bit key)
+constexpr int MAX_CS = 8;            // portable cluster size
+constexpr int MAX_SLICE = 36864;     // ids per CTA kept in shared memory (144 KB)
+
+// Control block at the start of dynamic shared memory; the CTA's slice of exp'd logits follows it.
+struct __align__(16) SampShared {
+  uint32_t h1_lo[SBINS], h1_hi[SBINS];      // level-1 histogram, 32.32 fixed point split in two native-atomic words
+  uint32_t h2_lo[SBINS], h2_hi[SBINS];      // level-2 histogram (inside the boundary bin)
+  unsigned long long merged[SBINS];         // cluster-wide sum of the level being scanned
+  unsigned long long wsum[32];
+  unsigned long long red_u[32];
+  unsigned long long cz[MAX_CS];            // per-CTA partition-function partials (written by every peer)
+  float cmax[MAX_CS];
+  int camx[MAX_CS];
+  float ctot[MAX_CS];                       // per-CTA kept mass
+  float red_f[32];
+  int red_i[32];
+  float wtot[32];
+  unsigned long long s_u[2];
+  int s_i[4];
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
 }
 
-__global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SampleParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float red_f[32];
-  __shared__ int red_i[32];
-  __shared__ uint32_t hist_lo[NBINS];     // 32.32 fixed-point mass per bin: native ATOMS.ADD on the
-  __shared__ uint32_t hist_hi[NBINS];     // low word, carries (rare) bump the high word
-  __shared__ unsigned long long red_u[32];
-  __shared__ unsigned long long s_u[2];
-  __shared__ float s_bcast[4];
-  __shared__ int s_ib[4];
+// monotone 28-bit key of e in [2^-32, 1]: 5 exponent bits + 23 mantissa bits (smaller e -> 0)
+__device__ __forceinline__ uint32_t dkey(float e) {
+  const uint32_t u = __float_as_uint(e);
+  return u < 0x2F800000u ? 0u : min(u - 0x2F800000u, 0x0FFFFFFFu);
+}
+__device__ __forceinline__ uint32_t fx32(float e) { return static_cast<uint32_t>(fminf(e * 4294967296.0f, 4294967040.0f)); }
+__device__ __forceinline__ void hist_add(uint32_t* lo, uint32_t* hi, int bin, uint32_t f) {
+  const uint32_t old = atomicAdd(&lo[bin], f);
+  if (old + f < old) atomicAdd(&hi[bin], 1u);
+}
+
+// One CLUSTER of CS CTAs per sequence (grid = [B, 1, CS]); CTA r owns ids [r*W, (r+1)*W).  A single
+// SM is instruction-bound on a 128k vocabulary (about 28 us per pass, profiles/bench_history.md), so the
+// vocabulary is spread over CS SMs, each slice is read from L2 exactly once and then lives in shared
+// memory as exp(l - max); the per-level histograms are merged across the cluster through DSMEM.
+__global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SampleParams p, const int W) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SampShared& S = *reinterpret_cast<SampShared*>(smem_raw);
+  float* ebuf = reinterpret_cast<float*>(smem_raw + sizeof(SampShared));
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int CS = gridDim.z, r = blockIdx.z;
+  pdl_launch_dependents();
+  for (int i = tid; i < SBINS; i += SAMP_THREADS) { S.h1_lo[i] = 0u; S.h1_hi[i] = 0u; S.h2_lo[i] = 0u; S.h2_hi[i] = 0u; }
+  pdl_wait();
+
   const int bb = (p.row_base != nullptr ? p.row_base[0] : 0) + b;     // row of the per-sequence state
   const int V = p.vocab;
   const float* logits = p.logits + static_cast<size_t>(b) * p.ld;
@@ -118,171 +118,15 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
   uint32_t* seen = p.seen ? p.seen + static_cast<size_t>(bb) * ((V + 31) / 32) : nullptr;
   const float temp = p.temperature ? p.temperature[bb] : 0.f;
   const float pen = p.rep_penalty ? p.rep_penalty[bb] : 1.f;
-  const float top_p = p.top_p ? p.top_p[bb] : 1.f;
+  const float top_p = p.top_p ? fminf(p.top_p[bb], 1.f) : 1.f;
   const bool greedy = !(temp > 0.f);
   const float inv_temp = greedy ? 1.f : 1.f / temp;
   const uint32_t* seen_r = (pen != 1.f) ? seen : nullptr;
+  const int lo = min(V, r * W), hi = min(V, lo + W), n = hi - lo;
+  const int n4 = n >> 2;
 
-  // ---- pass 1: max (+ argmax, lowest id on ties)
-  float mx = -INFINITY; int amx = 0;
-  visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap,
-        [&](int i, float l) { if (l > mx) { mx = l; amx = i; } });
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
-    if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
-  }
-  if (lane == 0) { red_f[warp] = mx; red_i[warp] = amx; }
-  __syncthreads();
-  if (warp == 0) {
-    mx = red_f[lane]; amx = red_i[lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
-      if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
-    }
-    if (lane == 0) { s_bcast[0] = mx; s_ib[0] = amx; }
-  }
-  __syncthreads();
-  mx = s_bcast[0];
-  int token = s_ib[0];
-
-  if (!greedy) {
-    auto fx = [](float e) { return static_cast<uint32_t>(fminf(e * 4294967296.0f, 4294967040.0f)); };
-    auto hist_add = [&](int bin, uint32_t f) {
-      const uint32_t old = atomicAdd(&hist_lo[bin], f);
-      if (old + f < old) atomicAdd(&hist_hi[bin], 1u);
-    };
-    auto hist_get = [&](int bin) { return (static_cast<unsigned long long>(hist_hi[bin]) << 32) | hist_lo[bin]; };
-    // top-down scan of the histogram (warp 0): highest bin whose suffix mass (plus carry) reaches `need`;
-    // above = mass strictly above that bin, incl = mass including it.
-    auto scan_down = [&](unsigned long long carry, unsigned long long need, int& found, unsigned long long& above,
-                         unsigned long long& incl) {
-      found = -1; above = carry; incl = carry;
-      for (int base = NBINS - 32; base >= 0 && found < 0; base -= 32) {
-        const unsigned long long v = hist_get(base + (31 - lane));     // lane 0 = highest bin of the chunk
-        unsigned long long pre = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
-        const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
-        if (ball) {
-          const int l0 = __ffs(ball) - 1;
-          found = base + (31 - l0);
-          incl = carry + __shfl_sync(0xffffffffu, pre, l0);
-          above = incl - __shfl_sync(0xffffffffu, v, l0);
-        } else {
-          carry += __shfl_sync(0xffffffffu, pre, 31);
-          incl = carry;
-        }
-      }
-    };
-
-    // ---- pass 2: level-1 histogram of e = exp(l - max) in (0, 1]; key = top 12 bits below the sign
-    for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
-    __syncthreads();
-    unsigned long long zsum = 0ull;
-    visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap, [&](int, float l) {
-      const float e = __expf(l - mx);
-      const uint32_t f = fx(e);
-      zsum += f;
-      hist_add(__float_as_uint(e) >> 19, f);
-    });
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
-    if (lane == 0) red_u[warp] = zsum;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long z = red_u[lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-      if (lane == 0) s_u[0] = z;
-    }
-    __syncthreads();
-    const unsigned long long Z = s_u[0];
-    const unsigned long long need = static_cast<unsigned long long>(static_cast<double>(top_p) * static_cast<double>(Z));
-    if (warp == 0) {
-      int found; unsigned long long above, incl;
-      scan_down(0ull, need, found, above, incl);
-      if (lane == 0) { s_ib[1] = found < 0 ? 0 : found; s_u[1] = found < 0 ? 0ull : above; }
-    }
-    __syncthreads();
-    const int B1 = s_ib[1];
-    const unsigned long long above1 = s_u[1];       // mass strictly above the boundary bin
-
-    // ---- pass 3: level-2 histogram inside the boundary bin (next 12 bits)
-    for (int i = tid; i < NBINS; i += SAMP_THREADS) { hist_lo[i] = 0u; hist_hi[i] = 0u; }
-    __syncthreads();
-    visit(logits, seen_r, 0, V, tid, SAMP_THREADS, vec_ok, pen, inv_temp, cap, [&](int, float l) {
-      const float e = __expf(l - mx);
-      const uint32_t u = __float_as_uint(e);
-      if (static_cast<int>(u >> 19) == B1) hist_add((u >> 7) & (NBINS - 1), fx(e));
-    });
-    __syncthreads();
-    if (warp == 0) {
-      int found; unsigned long long above, incl;
-      scan_down(above1, need, found, above, incl);
-      if (found < 0) found = 0;
-      if (lane == 0) { s_ib[2] = found; s_bcast[3] = static_cast<float>(static_cast<double>(incl) * (1.0 / 4294967296.0)); }
-    }
-    __syncthreads();
-    const uint32_t thr_bits = (static_cast<uint32_t>(B1) << 19) | (static_cast<uint32_t>(s_ib[2]) << 7);
-    const float kept_mass = s_bcast[3];    // total mass of tokens with bits(e) >= thr_bits
-
-    // ---- pass 4: multinomial draw over the kept set, in index order
-    const uint32_t stepv = p.step ? *p.step : 0u;
-    const uint32_t h = hash_u32((p.seeds ? p.seeds[bb] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
-    const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float target = u01 * kept_mass;
-    // one contiguous chunk per WARP (multiple of 128 ids), lanes own interleaved quads -> coalesced 128-bit reads
-    const int cw = ((V + 31) / 32 + 127) & ~127;
-    const int c0 = warp * cw, c1 = min(V, c0 + cw);
-    float mine = 0.f;
-    if (c0 < c1)
-      visit(logits, seen_r, c0, c1, lane, 32, vec_ok, pen, inv_temp, cap, [&](int, float l) {
-        const float e = __expf(l - mx);
-        if (__float_as_uint(e) >= thr_bits) mine += e;
-      });
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);   // warp total
-    if (lane == 0) red_f[warp] = mine;
-    if (tid == 0) s_ib[3] = -1;
-    __syncthreads();
-    float wtot = red_f[lane], wpre = wtot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, wpre, o); if (lane >= o) wpre += n; }
-    const float my_excl = __shfl_sync(0xffffffffu, wpre - wtot, warp);
-    const float my_tot = __shfl_sync(0xffffffffu, wtot, warp);
-    if (my_tot > 0.f && target >= my_excl && target < my_excl + my_tot) {
-      // the selected warp walks its chunk in rows of 32 consecutive ids with a warp prefix sum
-      float run = my_excl;
-      int pick = -1, last_kept = -1;
-      for (int base = c0; base < c1 && pick < 0; base += 32) {
-        const int i = base + lane;
-        float v = 0.f;
-        if (i < c1) {
-          const bool sn = seen_r ? ((seen_r[i >> 5] >> (i & 31)) & 1u) : false;
-          const float e = __expf(transform(logits[i], sn, pen, inv_temp, cap) - mx);
-          if (__float_as_uint(e) >= thr_bits) v = e;
-        }
-        float pre = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += n; }
-        const unsigned kept = __ballot_sync(0xffffffffu, v > 0.f);
-        if (kept) last_kept = base + (31 - __clz(kept));
-        const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && run + pre > target);
-        if (hit) pick = base + (__ffs(hit) - 1);
-        run += __shfl_sync(0xffffffffu, pre, 31);
-      }
-      if (pick < 0) pick = last_kept;          // float round-off at the chunk edge
-      if (lane == 0 && pick >= 0) atomicMax(&s_ib[3], pick);
-    }
-    __syncthreads();
-    if (s_ib[3] >= 0) token = s_ib[3];   // else (round-off at the far edge): fall back to argmax
-  }
-
-  if (tid == 0) {
+  // exactly one thread per sequence publishes the token
+  auto publish = [&](int token) {
     p.out_tokens[bb] = token;
     if (seen != nullptr) atomicOr(&seen[token >> 5], 1u << (token & 31));
     if (p.history != nullptr) {
@@ -302,7 +146,272 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
         st_release_sys(p.signal_flag, e);
       }
     }
+  };
+
+  // ---- phase 1: L2 -> (soft-cap, penalty, temperature) -> shared memory; running max / argmax
+  float mx = -INFINITY; int amx = 0;
+  {
+    auto take = [&](int i, float raw, uint32_t sw) {
+      const float l = transform(raw, (sw >> (i & 31)) & 1u, pen, inv_temp, cap);
+      ebuf[i - lo] = l;
+      if (l > mx) { mx = l; amx = i; }
+    };
+    for (int q = tid; q < n4; q += 2 * SAMP_THREADS) {
+      const int q2 = q + SAMP_THREADS;
+      const bool has2 = q2 < n4;
+      const int i0 = lo + 4 * q, i1 = lo + 4 * q2;
+      float a[4], c[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec_ok) {
+        const float4 va = *reinterpret_cast<const float4*>(logits + i0);
+        a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+        if (has2) {
+          const float4 vc = *reinterpret_cast<const float4*>(logits + i1);
+          c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = logits[i0 + k];
+        if (has2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) c[k] = logits[i1 + k];
+        }
+      }
+      const uint32_t sa = seen_r ? seen_r[i0 >> 5] : 0u;
+      const uint32_t sc = (seen_r && has2) ? seen_r[i1 >> 5] : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) take(i0 + k, a[k], sa);
+      if (has2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) take(i1 + k, c[k], sc);
+      }
+    }
+    for (int i = lo + 4 * n4 + tid; i < hi; i += SAMP_THREADS) take(i, logits[i], seen_r ? seen_r[i >> 5] : 0u);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
+    if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
+  }
+  if (lane == 0) { S.red_f[warp] = mx; S.red_i[warp] = amx; }
+  __syncthreads();
+  if (warp == 0) {
+    mx = S.red_f[lane]; amx = S.red_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, amx, o);
+      if (om > mx || (om == mx && oi < amx)) { mx = om; amx = oi; }
+    }
+    if (lane < CS) {       // every peer (and this CTA) gets this CTA's partial
+      st_dsmem_f32(mapa_smem(smem_u32(&S.cmax[r]), lane), mx);
+      st_dsmem_u32(mapa_smem(smem_u32(&S.camx[r]), lane), static_cast<uint32_t>(amx));
+    }
+  }
+  cluster_sync_all();
+  mx = S.cmax[0];
+  int token = S.camx[0];
+  for (int c = 1; c < CS; ++c)
+    if (S.cmax[c] > mx) { mx = S.cmax[c]; token = S.camx[c]; }      // ties keep the lower rank = lower id
+
+  if (greedy) {
+    if (r == 0 && tid == 0) publish(token);
+    return;
+  }
+
+  // ---- phase 2: e = exp(l - max) in place; level-1 histogram (top 11 key bits) and partition function
+  unsigned long long zsum = 0ull;
+  {
+    float4* e4 = reinterpret_cast<float4*>(ebuf);
+    for (int q = tid; q < n4; q += SAMP_THREADS) {
+      float4 v = e4[q];
+      v.x = __expf(v.x - mx); v.y = __expf(v.y - mx); v.z = __expf(v.z - mx); v.w = __expf(v.w - mx);
+      e4[q] = v;
+      const float ev[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t f = fx32(ev[k]);
+        zsum += f;
+        hist_add(S.h1_lo, S.h1_hi, dkey(ev[k]) >> 17, f);
+      }
+    }
+    for (int j = 4 * n4 + tid; j < n; j += SAMP_THREADS) {
+      const float e = __expf(ebuf[j] - mx);
+      ebuf[j] = e;
+      const uint32_t f = fx32(e);
+      zsum += f;
+      hist_add(S.h1_lo, S.h1_hi, dkey(e) >> 17, f);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+  if (lane == 0) S.red_u[warp] = zsum;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long z = S.red_u[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (lane < CS) st_dsmem_u64(mapa_smem(smem_u32(&S.cz[r]), lane), z);
+  }
+  cluster_sync_all();
+
+  // cluster-wide histogram -> S.merged (every CTA computes the same sum), then a top-down search for the
+  // highest bin whose suffix mass (plus `carry`) reaches `need`.  Results: s_i[0] = bin, s_u[0] = mass above it.
+  auto merge_and_find = [&](uint32_t* hlo, uint32_t* hhi, unsigned long long carry, unsigned long long need) {
+    {
+      const int bin = 2 * tid;        // SBINS == 2 * SAMP_THREADS
+      unsigned long long m0 = 0ull, m1 = 0ull;
+      const uint32_t alo = smem_u32(&hlo[bin]), ahi = smem_u32(&hhi[bin]);
+      for (int c = 0; c < CS; ++c) {
+        const uint2 l2 = ld_dsmem_v2u32(mapa_smem(alo, c));
+        const uint2 h2 = ld_dsmem_v2u32(mapa_smem(ahi, c));
+        m0 += (static_cast<unsigned long long>(h2.x) << 32) | l2.x;
+        m1 += (static_cast<unsigned long long>(h2.y) << 32) | l2.y;
+      }
+      S.merged[bin] = m0; S.merged[bin + 1] = m1;
+      unsigned long long ws = m0 + m1;      // warp w covers bins [64w, 64w + 64)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+      if (lane == 0) S.wsum[warp] = ws;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane l looks at warp-chunk 31 - l (highest bins first)
+      const unsigned long long v = S.wsum[31 - lane];
+      unsigned long long pre = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+      const unsigned ball = __ballot_sync(0xffffffffu, carry + pre >= need);
+      int found = -1;
+      unsigned long long above = carry;
+      if (ball) {
+        const int l0 = __ffs(ball) - 1;
+        unsigned long long run = carry + __shfl_sync(0xffffffffu, pre, l0) - __shfl_sync(0xffffffffu, v, l0);
+        const int cbase = (31 - l0) * 64;
+        for (int base = cbase + 32; base >= cbase && found < 0; base -= 32) {
+          const unsigned long long bv = S.merged[base + (31 - lane)];
+          unsigned long long bp = bv;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, bp, o); if (lane >= o) bp += t; }
+          const unsigned hit = __ballot_sync(0xffffffffu, run + bp >= need);
+          if (hit) {
+            const int l1 = __ffs(hit) - 1;
+            found = base + (31 - l1);
+            above = run + __shfl_sync(0xffffffffu, bp, l1) - __shfl_sync(0xffffffffu, bv, l1);
+          } else {
+            run += __shfl_sync(0xffffffffu, bp, 31);
+          }
+        }
+      }
+      if (lane == 0) { S.s_i[0] = found < 0 ? 0 : found; S.s_u[0] = found < 0 ? carry : above; }
+    }
+    __syncthreads();
+  };
+
+  unsigned long long Z = 0ull;
+  for (int c = 0; c < CS; ++c) Z += S.cz[c];
+  const unsigned long long need = static_cast<unsigned long long>(static_cast<double>(top_p) * static_cast<double>(Z));
+  merge_and_find(S.h1_lo, S.h1_hi, 0ull, need);
+  const int B1 = S.s_i[0];
+  const unsigned long long above1 = S.s_u[0];       // mass strictly above the boundary bin
+  __syncthreads();                                   // s_i / merged are reused by the second level
+
+  // ---- phase 3: level-2 histogram inside the boundary bin (next 11 key bits)
+  {
+    const float4* e4 = reinterpret_cast<const float4*>(ebuf);
+    for (int q = tid; q < n4; q += SAMP_THREADS) {
+      const float4 v = e4[q];
+      const float ev[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t d = dkey(ev[k]);
+        if (static_cast<int>(d >> 17) == B1) hist_add(S.h2_lo, S.h2_hi, (d >> 6) & (SBINS - 1), fx32(ev[k]));
+      }
+    }
+    for (int j = 4 * n4 + tid; j < n; j += SAMP_THREADS) {
+      const uint32_t d = dkey(ebuf[j]);
+      if (static_cast<int>(d >> 17) == B1) hist_add(S.h2_lo, S.h2_hi, (d >> 6) & (SBINS - 1), fx32(ebuf[j]));
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  merge_and_find(S.h2_lo, S.h2_hi, above1, need);
+  const uint32_t thr = (static_cast<uint32_t>(B1) << 17) | (static_cast<uint32_t>(S.s_i[0]) << 6);
+
+  // ---- phase 4: multinomial draw over the kept set {dkey(e) >= thr}, in id order.
+  // warp w owns a contiguous chunk of this CTA's slice; lanes own interleaved quads.
+  const int cw = ((n + 31) / 32 + 127) & ~127;
+  const int c0 = min(n, warp * cw), c1 = min(n, c0 + cw);
+  float mine = 0.f;
+  {
+    const float4* e4 = reinterpret_cast<const float4*>(ebuf + c0);
+    const int nq = (c1 - c0) >> 2;
+    for (int q = lane; q < nq; q += 32) {
+      const float4 v = e4[q];
+      if (dkey(v.x) >= thr) mine += v.x;
+      if (dkey(v.y) >= thr) mine += v.y;
+      if (dkey(v.z) >= thr) mine += v.z;
+      if (dkey(v.w) >= thr) mine += v.w;
+    }
+    for (int j = c0 + 4 * nq + lane; j < c1; j += 32)
+      if (dkey(ebuf[j]) >= thr) mine += ebuf[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) S.wtot[warp] = mine;
+  __syncthreads();
+  // inclusive prefix over the 32 warp totals (every warp computes the same values)
+  const float wt = S.wtot[lane];
+  float wpre = wt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, wpre, o); if (lane >= o) wpre += t; }
+  const float cta_total = __shfl_sync(0xffffffffu, wpre, 31);
+  if (warp == 0 && lane < CS) st_dsmem_f32(mapa_smem(smem_u32(&S.ctot[r]), lane), cta_total);
+  cluster_sync_all();                 // last remote access of the kernel (also fences the DSMEM histogram reads)
+
+  float kept_total = 0.f, my_excl = 0.f;
+  for (int c = 0; c < CS; ++c) { if (c == r) my_excl = kept_total; kept_total += S.ctot[c]; }
+  const uint32_t stepv = p.step ? *p.step : 0u;
+  const uint32_t h = hash_u32((p.seeds ? p.seeds[bb] : 0x1234567u) ^ hash_u32(stepv * 0x9E3779B9u + b));
+  const float u01 = (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float target = u01 * kept_total;
+  // the owner is the LAST non-empty CTA whose exclusive prefix is <= target (absorbs float round-off at the far edge)
+  int owner = -1;
+  {
+    float run = 0.f;
+    for (int c = 0; c < CS; ++c) {
+      if (S.ctot[c] > 0.f && (run <= target || owner < 0)) owner = c;
+      run += S.ctot[c];
+    }
+  }
+  if (owner < 0) {                    // only reachable with NaN logits: fall back to the arg-max
+    if (r == 0 && tid == 0) publish(token);
+    return;
+  }
+  if (owner != r) return;
+  // same rule for the warp inside the CTA
+  const float w_excl = my_excl + (wpre - wt);
+  const unsigned cand = __ballot_sync(0xffffffffu, wt > 0.f && w_excl <= target);
+  const unsigned nonempty = __ballot_sync(0xffffffffu, wt > 0.f);
+  const int wsel = cand ? (31 - __clz(cand)) : (__ffs(nonempty) - 1);
+  if (warp != wsel) return;
+  float run = my_excl + __shfl_sync(0xffffffffu, wpre - wt, wsel);
+  int pick = -1, last_kept = -1;
+  for (int base = c0; base < c1 && pick < 0; base += 32) {
+    const int j = base + lane;
+    float v = 0.f;
+    if (j < c1) { const float e = ebuf[j]; if (dkey(e) >= thr) v = e; }
+    float pre = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+    const unsigned kept = __ballot_sync(0xffffffffu, v > 0.f);
+    if (kept) last_kept = base + (31 - __clz(kept));
+    const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && run + pre > target);
+    if (hit) pick = base + (__ffs(hit) - 1);
+    run += __shfl_sync(0xffffffffu, pre, 31);
+  }
+  if (pick < 0) pick = last_kept;
+  if (lane == 0) publish(pick >= 0 ? lo + pick : token);
 }
 
 // mark prompt tokens in the seen bitmap: ids [n], seq_of [n]
@@ -326,7 +435,23 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
   p.hist_pos = hist_pos; p.hist_pos_out = hist_pos_out; p.hist_stride = hist_stride; p.vocab = vocab; p.ld = ld; p.softcap = softcap;
   p.temperature = temperature; p.top_p = top_p; p.rep_penalty = rep_penalty; p.seeds = seeds; p.step = step;
   p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter; p.row_base = row_base;
-  return static_cast<int>(launch_kernel(sample_kernel, dim3(batch), dim3(SAMP_THREADS), 0, s, 1, p));
+  // cluster size: the slice must fit in shared memory; beyond that use more SMs while the grid is below one wave
+  int cs = 1;
+  while (cs < MAX_CS && (vocab + cs - 1) / cs > MAX_SLICE) cs *= 2;
+  if ((vocab + cs - 1) / cs > MAX_SLICE) return -6;
+  while (cs < MAX_CS && batch * cs * 2 <= 148) cs *= 2;
+  const int W = (((vocab + cs - 1) / cs) + 127) & ~127;
+  const size_t smem = sizeof(SampShared) + static_cast<size_t>(W) * sizeof(float);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    const cudaError_t e = cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(sizeof(SampShared) + MAX_SLICE * sizeof(float)));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev] = true;
+  }
+  return static_cast<int>(launch_kernel(sample_kernel, dim3(batch, 1, cs), dim3(SAMP_THREADS), smem, s, cs, p, W));
 }
 
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s) {
