@@ -220,6 +220,15 @@ def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, 
     return out
 
 
+def set_attn_tc_min_q(n: int) -> None:
+    """Query-chunk length from which prefill attention runs on the tcgen05 kernel (0 = scalar kernel only)."""
+    native().set_attn_tc_min_q(int(n))
+
+
+def get_attn_tc_min_q() -> int:
+    return int(native().get_attn_tc_min_q())
+
+
 # ---------------------------------------------------------------------- sampler
 def sample(logits, out_tokens, *, seen=None, temperature=None, top_p=None, rep_penalty=None, seeds=None, step=None,
            peer_tokens=0, history=0, hist_pos=None, hist_stride=0, signal_flag=0, signal_epoch=0, done_counter=0,

@@ -1,0 +1,434 @@
+// Prefill (and chunked-prefill) attention on the 5th-gen tensor cores: flash-attention forward over
+// the paged KV cache with tcgen05.mma, accumulators in TMEM, operands staged by TMA.
+//
+// One CTA = (sequence, kv head, block of QB = 128/G queries).  The G query heads that share the kv
+// head are stacked into the 128 MMA rows (row = g*QB + i), so every K/V page is fetched once per
+// group.  Per KV tile of BKV keys:
+//     S = Q K^T      tcgen05.mma  (A = Q tile, B = K tile, both K-major 128B-swizzled)  -> TMEM, double buffered
+//     P = softmax    4 warps, one TMEM lane (= row) per thread, online max with lazy rescaling
+//     O += P V       tcgen05.mma  (A = P written to swizzled smem as bf16, B = V tile read MN-major:
+//                                  the cache keeps V as [token, d], i.e. N-contiguous)
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = softmax / correction / epilogue.
+// q is pre-scaled by 1/sqrt(d) and rotated by the QKV GEMM epilogue; K is rotated when appended.
+//
+// Layouts: q/out [tokens, n_q, D]; K/V cache [pages, 64, n_kv, D]; block_table [seqs, max_pages].
+// Reference parity: torch SDPA under `transformers.generate` (bee2bee/hf.py:42-43).
+#include "kernels.h"
+
+#include <cuda.h>
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace b2b {
+
+int make_tmap_shared(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     int elt_bytes);
+
+namespace {
+
+constexpr int APAGE = 64;
+constexpr int ATC_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  const int* block_table;
+  const int* q_start;
+  const int* q_len;
+  const int* kv_len;
+  int max_pages, n_q, n_kv, window;
+  float softcap;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+      "%31,%32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])),
+        "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])),
+        "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])),
+        "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// MN-major 128B-swizzled operand (rows = K index, 128-byte rows of 64 contiguous N elements):
+// LBO = distance between 64-element N blocks, SBO = distance between 8-row K groups (1024 B).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int D, int BKV>
+struct AtcCfg {
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = BKV * D * 2;
+  static constexpr int kPBytes = 128 * BKV * 2;
+  static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + kPBytes + 256 + 1024;   // + barriers + alignment slack
+};
+
+template <int D, int BKV, bool SOFTCAP>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                       const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p, const int G, const int QB) {
+  using Cfg = AtcCfg<D, BKV>;
+  constexpr int DB = D / 64;            // 64-column (128 B) blocks of the head dim
+  constexpr int PB = BKV / 64;          // 64-key blocks of a KV tile == pages per tile
+  constexpr uint32_t S_COL = 0, O_COL = 256;
+
+  pdl_launch_dependents();
+  pdl_wait();                                               // the metadata below may come from an earlier kernel
+  const int seq = blockIdx.z, kvh = blockIdx.y;
+  const int qblk = gridDim.x - 1 - blockIdx.x;             // longest (latest) query blocks first
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = qblk * QB;
+  if (q0 >= qlen) return;
+  const int nq_here = min(QB, qlen - q0);
+  const int qtok0 = p.q_start[seq] + q0;
+  const int pos0 = kvlen - qlen + q0;                       // absolute position of query 0 of this block
+  const int kv_hi = min(kvlen, pos0 + nq_here);
+  const int kv_lo = p.window > 0 ? max(0, pos0 - p.window + 1) : 0;
+  const int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
+  const int nt = t_hi - t_lo;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + Cfg::kQBytes;                       // [2][kKVBytes]
+  uint8_t* v_s = k_s + 2 * Cfg::kKVBytes;                  // [2][kKVBytes]
+  uint8_t* p_s = v_s + 2 * Cfg::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + Cfg::kPBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [2]
+  uint64_t* k_empty = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;     // [2]
+  uint64_t* p_ready = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+      for (int g = 0; g < G; ++g)
+        for (int c = 0; c < DB; ++c)
+          tma_load_2d(q_s + c * (128 * 128) + g * QB * 128, &tm_q, q_full, (kvh * G + g) * D + c * 64, qtok0);
+      const int* bt = p.block_table + static_cast<size_t>(seq) * p.max_pages;
+      const int last_page = (kvlen - 1) / APAGE;
+      for (int n = 0; n < nt; ++n) {
+        const int t = t_lo + n, s = n & 1;
+        const uint32_t ph = static_cast<uint32_t>((n >> 1) & 1);
+        int pages[PB];
+#pragma unroll
+        for (int pg = 0; pg < PB; ++pg) pages[pg] = bt[min(t * PB + pg, last_page)];
+        mbar_wait(&k_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&k_full[s], Cfg::kKVBytes);
+#pragma unroll
+        for (int pg = 0; pg < PB; ++pg)
+#pragma unroll
+          for (int c = 0; c < DB; ++c)
+            tma_load_2d(k_s + s * Cfg::kKVBytes + c * (BKV * 128) + pg * (APAGE * 128), &tm_k, &k_full[s],
+                        kvh * D + c * 64, pages[pg] * APAGE);
+        mbar_wait(&v_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&v_full[s], Cfg::kKVBytes);
+#pragma unroll
+        for (int pg = 0; pg < PB; ++pg)
+#pragma unroll
+          for (int c = 0; c < DB; ++c)
+            tma_load_2d(v_s + s * Cfg::kKVBytes + c * (BKV * 128) + pg * (APAGE * 128), &tm_v, &v_full[s],
+                        kvh * D + c * 64, pages[pg] * APAGE);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, D) | (1u << 16);        // B operand (V) is MN-major
+    auto issue_qk = [&](int n) {
+      const int s = n & 1;
+      mbar_wait(&k_full[s], static_cast<uint32_t>((n >> 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem + S_COL + static_cast<uint32_t>(s) * BKV;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t a = make_sw128_kmajor_desc(smem_u32(q_s + (kk / 4) * (128 * 128))) + static_cast<uint64_t>((kk % 4) * 2);
+          const uint64_t b = make_sw128_kmajor_desc(smem_u32(k_s + s * Cfg::kKVBytes + (kk / 4) * (BKV * 128))) +
+                             static_cast<uint64_t>((kk % 4) * 2);
+          umma_bf16(d_tmem, a, b, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    if (nt > 0) issue_qk(0);
+    for (int n = 0; n < nt; ++n) {
+      if (n + 1 < nt) issue_qk(n + 1);                    // S(n+1) runs on the tensor pipe while softmax(n) runs
+      const int s = n & 1;
+      mbar_wait(&v_full[s], static_cast<uint32_t>((n >> 1) & 1));
+      mbar_wait(p_ready, static_cast<uint32_t>(n & 1));
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t a = make_sw128_kmajor_desc(smem_u32(p_s + (kk / 4) * (128 * 128))) + static_cast<uint64_t>((kk % 4) * 2);
+          const uint64_t b = make_sw128_mnmajor_desc(smem_u32(v_s + s * Cfg::kKVBytes + kk * (16 * 128)), BKV * 128);
+          umma_bf16(tmem + O_COL, a, b, idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int g = row / QB, i = row % QB;
+    const bool row_valid = (g < G) && (i < nq_here);
+    const int qpos = pos0 + i;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float cap = p.softcap;
+    float m_ref = -INFINITY, l = 0.f;
+
+    const float inv_cap = SOFTCAP ? 1.f / cap : 0.f;
+    // raw score -> (soft-cap) -> log2 domain; MASKED tiles also apply the causal / window / length predicate
+    auto score = [&](float s, int kvpos, auto masked) {
+      if constexpr (SOFTCAP) s = cap * tanhf(s * inv_cap);
+      s *= LOG2E;
+      if constexpr (decltype(masked)::value) {
+        const bool ok = row_valid && kvpos <= qpos && kvpos < kvlen && (p.window <= 0 || kvpos > qpos - p.window);
+        return ok ? s : -INFINITY;
+      } else {
+        return s;
+      }
+    };
+
+    auto tile = [&](int n, auto masked) {
+      const int t = t_lo + n, b = n & 1;
+      mbar_wait(&s_full[b], static_cast<uint32_t>((n >> 1) & 1));
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + S_COL + static_cast<uint32_t>(b) * BKV;
+      // pass 1: row maximum (log2 domain)
+      float mrow = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mrow = fmaxf(mrow, score(v[e], t * BKV + c + e, masked));
+      }
+      // lazy rescaling: keep the reference max while the new maximum is within 2^8 of it
+      float alpha = 1.f;
+      if (mrow > m_ref + 8.f || (m_ref == -INFINITY && mrow > -INFINITY)) {
+        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - mrow);
+        m_ref = mrow;
+      }
+      if (n > 0) {
+        mbar_wait(pv_done, static_cast<uint32_t>((n - 1) & 1));        // P smem and O are free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < D; c += 32) {
+            float o[32];
+            tmem_ld32(lane_addr + O_COL + c, o);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] *= alpha;
+            tmem_st32(lane_addr + O_COL + c, o);
+          }
+        }
+      }
+      l *= alpha;
+      // pass 2: P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile (A operand of the PV MMA)
+      const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;          // fully masked so far: exp2(-inf - 0) = 0
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = exp2f(score(v[e], t * BKV + c + e, masked) - mr);
+          const float p1 = exp2f(score(v[e + 1], t * BKV + c + e + 1, masked) - mr);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          lsum += __low2float(h) + __high2float(h);
+          packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint8_t* ptile = p_s + (c >> 6) * (128 * 128) + row * 128;
+        const int ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = (ch0 + j) ^ (row & 7);
+          *reinterpret_cast<uint4*>(ptile + ch * 16) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      l += lsum;
+      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    };
+
+    for (int n = 0; n < nt; ++n) {
+      const int t = t_lo + n;
+      // a tile needs no predicate when every key of it is visible to every (valid) query row of the block
+      const bool full = nq_here == QB && (t + 1) * BKV - 1 <= pos0 && (t + 1) * BKV <= kvlen &&
+                        (p.window <= 0 || t * BKV > pos0 + nq_here - 1 - p.window);
+      if (full) tile(n, std::false_type{}); else tile(n, std::true_type{});
+    }
+
+    // epilogue: O / l -> out[token, head, :]
+    if (nt > 0) {
+      mbar_wait(pv_done, static_cast<uint32_t>((nt - 1) & 1));
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* dst = p.out + (static_cast<size_t>(qtok0 + i) * p.n_q + kvh * G + g) * D;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      float o[32];
+      if (nt > 0) {
+        tmem_ld32(lane_addr + O_COL + c, o);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = 0.f;
+      }
+      if (row_valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(o[8 * j + 2 * e] * inv, o[8 * j + 2 * e + 1] * inv);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(dst + c + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int D, int BKV, bool SOFTCAP>
+int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
+              int seqs, int qblocks, cudaStream_t s) {
+  using Cfg = AtcCfg<D, BKV>;
+  static bool set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D, BKV, SOFTCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    set[dev] = true;
+  }
+  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, BKV, SOFTCAP>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
+                                        Cfg::kSmemBytes, s, 1, tq, tk, tv, p, G, QB));
+}
+
+template <int D, int BKV>
+int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
+              int seqs, int qblocks, cudaStream_t s) {
+  return p.softcap > 0.f ? launch_tc_cap<D, BKV, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
+                         : launch_tc_cap<D, BKV, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+}
+
+}  // namespace
+
+bool attention_tc_supported(int n_q, int n_kv, int head_dim) {
+  if (n_kv <= 0 || n_q % n_kv) return false;
+  const int G = n_q / n_kv;
+  if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16) return false;
+  return head_dim == 64 || head_dim == 128 || head_dim == 256;
+}
+
+// Prefill path: every sequence contributes q_len >= 1 new tokens, kv_len includes them.
+int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int* block_table,
+                        const int* q_start, const int* q_len, const int* kv_len, int seqs, int max_q, int max_pages,
+                        int n_tokens, int n_pages, int n_q, int n_kv, int head_dim, int window, float softcap,
+                        cudaStream_t s) {
+  if (!attention_tc_supported(n_q, n_kv, head_dim)) return -2;
+  const int G = n_q / n_kv, QB = 128 / G;
+  CUtensorMap tq, tk, tv;
+  int r = make_tmap_shared(&tq, q, static_cast<uint64_t>(n_tokens), static_cast<uint64_t>(n_q) * head_dim,
+                           static_cast<uint64_t>(n_q) * head_dim, static_cast<uint32_t>(QB), 2);
+  if (r) return r;
+  const uint64_t kv_rows = static_cast<uint64_t>(n_pages) * APAGE, kv_cols = static_cast<uint64_t>(n_kv) * head_dim;
+  if ((r = make_tmap_shared(&tk, k_cache, kv_rows, kv_cols, kv_cols, APAGE, 2))) return r;
+  if ((r = make_tmap_shared(&tv, v_cache, kv_rows, kv_cols, kv_cols, APAGE, 2))) return r;
+  AttnTcParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.block_table = block_table; p.q_start = q_start; p.q_len = q_len; p.kv_len = kv_len;
+  p.max_pages = max_pages; p.n_q = n_q; p.n_kv = n_kv; p.window = window; p.softcap = softcap;
+  const int qblocks = (max_q + QB - 1) / QB;
+  switch (head_dim) {
+    case 64: return launch_tc<64, 128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 128: return launch_tc<128, 128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 256: return launch_tc<256, 64>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    default: return -3;
+  }
+}
+
+}  // namespace b2b

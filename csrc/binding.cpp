@@ -215,6 +215,14 @@ void flag_signal(int64_t flag, int64_t epoch, int64_t bump_epoch, int64_t ack_fl
 }
 
 // -------------------------------------------------------------------- attention
+// query-chunk length from which the tensor-core prefill kernel is used (0 = never); env B2B_ATTN_TC_MIN_Q
+static int64_t g_attn_tc_min_q = [] {
+  const char* e = std::getenv("B2B_ATTN_TC_MIN_Q");
+  return e ? static_cast<int64_t>(std::atoi(e)) : static_cast<int64_t>(16);
+}();
+void set_attn_tc_min_q(int64_t v) { g_attn_tc_min_q = v; }
+int64_t get_attn_tc_min_q() { return g_attn_tc_min_q; }
+
 void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& out,
                const Tensor& block_table, const Tensor& q_start, const Tensor& q_len, const Tensor& kv_len,
                const OptT& ws, int64_t max_q, int64_t n_q, int64_t n_kv, int64_t head_dim, int64_t window,
@@ -223,6 +231,21 @@ void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, co
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(block_table.scalar_type() == at::kInt && q_len.scalar_type() == at::kInt, "int32 metadata expected");
   const int seqs = static_cast<int>(q_len.size(0));
+  if (max_q >= g_attn_tc_min_q && g_attn_tc_min_q > 0 &&
+      b2b::attention_tc_supported(static_cast<int>(n_q), static_cast<int>(n_kv), static_cast<int>(head_dim))) {
+    // prefill chunk: tcgen05 flash attention
+    check(b2b::launch_attention_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+                                   reinterpret_cast<const int*>(block_table.data_ptr()),
+                                   reinterpret_cast<const int*>(q_start.data_ptr()),
+                                   reinterpret_cast<const int*>(q_len.data_ptr()),
+                                   reinterpret_cast<const int*>(kv_len.data_ptr()), seqs, static_cast<int>(max_q),
+                                   static_cast<int>(block_table.size(1)), static_cast<int>(q.size(0)),
+                                   static_cast<int>(k_cache.size(0)), static_cast<int>(n_q), static_cast<int>(n_kv),
+                                   static_cast<int>(head_dim), static_cast<int>(window), static_cast<float>(softcap),
+                                   cur_stream()),
+          "attention_tc");
+    return;
+  }
   if (splits > 1) {
     TORCH_CHECK(ws.has_value(), "split-KV needs a workspace");
     const int64_t R = b2b::attn_rows(static_cast<int>(n_q / n_kv), 1);
@@ -343,6 +366,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flag_signal", &flag_signal);
   m.def("decode_advance", &decode_advance);
   m.def("attention", &attention);
+  m.def("set_attn_tc_min_q", &set_attn_tc_min_q);
+  m.def("get_attn_tc_min_q", &get_attn_tc_min_q);
   m.def("sample", &sample);
   m.def("mark_seen", &mark_seen);
   m.def("set_decode_state", &set_decode_state);

@@ -30,6 +30,12 @@ int launch_attention(const void* q, const void* k_cache, const void* v_cache, vo
                      int max_pages, int n_q, int n_kv, int head_dim, int window, float softcap, int splits,
                      cudaStream_t s);
 int attn_rows(int G, int QB);
+// attention_tc.cu: tcgen05 flash-attention forward for prefill chunks
+bool attention_tc_supported(int n_q, int n_kv, int head_dim);
+int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int* block_table,
+                        const int* q_start, const int* q_len, const int* kv_len, int seqs, int max_q, int max_pages,
+                        int n_tokens, int n_pages, int n_q, int n_kv, int head_dim, int window, float softcap,
+                        cudaStream_t s);
 int attention_init();
 
 // sampler.cu

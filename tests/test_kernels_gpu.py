@@ -256,6 +256,47 @@ def test_attention_prefill(hd, nq, nkv, window):
     close(out, _attn_ref(q, kc, vc, bt, q_lens, kv_lens, nq, nkv, hd, window, 0.0))
 
 
+def test_attention_prefill_scalar_fallback_kernel():
+    """The CUDA-core kernel (used for short chunks / unsupported head layouts) stays correct."""
+    hd, nq, nkv = 128, 8, 2
+    q_lens, kv_lens = [70, 1, 33, 16], [70, 9, 100, 16]
+    kc, vc, bt = _paged_setup(kv_lens, nkv, hd)
+    q = bf(sum(q_lens), nq * hd, scale=0.3)
+    out = torch.zeros_like(q)
+    qs = torch.tensor([0, 70, 71, 104], device="cuda", dtype=torch.int32)
+    ql = torch.tensor(q_lens, device="cuda", dtype=torch.int32)
+    kvl = torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
+    old = ops.get_attn_tc_min_q()
+    ops.set_attn_tc_min_q(0)
+    try:
+        ops.attention(q, kc, vc, out, bt, qs, ql, kvl, max_q=max(q_lens), n_q=nq, n_kv=nkv, head_dim=hd)
+    finally:
+        ops.set_attn_tc_min_q(old)
+    close(out, _attn_ref(q, kc, vc, bt, q_lens, kv_lens, nq, nkv, hd, 0, 0.0))
+
+
+@pytest.mark.parametrize("hd,nq,nkv,window,softcap", [
+    (128, 32, 8, 0, 0.0),        # Llama-3 / Mistral head layout
+    (128, 32, 8, 300, 0.0),      # sliding window (Mistral / Gemma-2 local layers)
+    (256, 8, 4, 0, 50.0),        # Gemma-2: d=256, soft-capping
+    (64, 12, 12, 0, 0.0),        # GPT-2: MHA, d=64
+])
+def test_attention_prefill_tcgen05_long(hd, nq, nkv, window, softcap):
+    """tcgen05 flash-attention prefill: long prompts, chunked prefill on top of cached context, ragged batch."""
+    q_lens = [1000, 257, 640]
+    kv_lens = [1000, 900, 640]         # sequence 1 is a second chunk on top of 643 cached tokens
+    kc, vc, bt = _paged_setup(kv_lens, nkv, hd)
+    q = bf(sum(q_lens), nq * hd, scale=0.3)
+    out = torch.zeros_like(q)
+    qs = torch.tensor([0, 1000, 1257], device="cuda", dtype=torch.int32)
+    ql = torch.tensor(q_lens, device="cuda", dtype=torch.int32)
+    kvl = torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
+    assert ops.get_attn_tc_min_q() > 0
+    ops.attention(q, kc, vc, out, bt, qs, ql, kvl, max_q=max(q_lens), n_q=nq, n_kv=nkv, head_dim=hd, window=window,
+                  softcap=softcap)
+    close(out, _attn_ref(q, kc, vc, bt, q_lens, kv_lens, nq, nkv, hd, window, softcap))
+
+
 # --------------------------------------------------------------------- sampler
 def test_sampler_greedy_and_penalty():
     B, V = 4, 1000
