@@ -91,22 +91,51 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
   return d;
 }
 
-template <int D, int BKV>
+// issue-only TMEM load of 32 columns (this thread's lane); pair with tmem_ld_fence() before reading r[]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for all outstanding TMEM loads; the "+r" operands keep every use of r[] after the wait
+__device__ __forceinline__ void tmem_ld_fence(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+template <int D>
 struct AtcCfg {
+  static constexpr int BKV = 64;                                  // keys per tile == one KV page
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = BKV * D * 2;
   static constexpr int kPBytes = 128 * BKV * 2;
-  static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + kPBytes + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + kPBytes + 256;
+  static constexpr int kTmemCols = (2 * BKV + D <= 256) ? 256 : 512;   // S double buffer + O
+  static constexpr int kMinCtas = (D <= 128) ? 2 : 1;                  // two CTAs per SM: one's softmax hides the other's MMAs
 };
 
-template <int D, int BKV, bool SOFTCAP>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+template <int D, bool SOFTCAP>
+__global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::kMinCtas)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p, const int G, const int QB) {
-  using Cfg = AtcCfg<D, BKV>;
+  using Cfg = AtcCfg<D>;
+  constexpr int BKV = Cfg::BKV;
   constexpr int DB = D / 64;            // 64-column (128 B) blocks of the head dim
-  constexpr int PB = BKV / 64;          // 64-key blocks of a KV tile == pages per tile
-  constexpr uint32_t S_COL = 0, O_COL = 256;
+  constexpr uint32_t S_COL = 0, O_COL = 2 * BKV;
+  constexpr uint32_t TCOLS = Cfg::kTmemCols;
 
   pdl_launch_dependents();
   pdl_wait();                                               // the metadata below may come from an earlier kernel
@@ -123,8 +152,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
   const int nt = t_hi - t_lo;
 
-  extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();             // the swizzled tiles need 1024-byte alignment
   uint8_t* q_s = smem;
   uint8_t* k_s = q_s + Cfg::kQBytes;                       // [2][kKVBytes]
   uint8_t* v_s = k_s + 2 * Cfg::kKVBytes;                  // [2][kKVBytes]
@@ -152,7 +181,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,29 +195,20 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         for (int c = 0; c < DB; ++c)
           tma_load_2d(q_s + c * (128 * 128) + g * QB * 128, &tm_q, q_full, (kvh * G + g) * D + c * 64, qtok0);
       const int* bt = p.block_table + static_cast<size_t>(seq) * p.max_pages;
-      const int last_page = (kvlen - 1) / APAGE;
       for (int n = 0; n < nt; ++n) {
-        const int t = t_lo + n, s = n & 1;
+        const int s = n & 1;
         const uint32_t ph = static_cast<uint32_t>((n >> 1) & 1);
-        int pages[PB];
-#pragma unroll
-        for (int pg = 0; pg < PB; ++pg) pages[pg] = bt[min(t * PB + pg, last_page)];
+        const int page = bt[t_lo + n];
         mbar_wait(&k_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kKVBytes);
 #pragma unroll
-        for (int pg = 0; pg < PB; ++pg)
-#pragma unroll
-          for (int c = 0; c < DB; ++c)
-            tma_load_2d(k_s + s * Cfg::kKVBytes + c * (BKV * 128) + pg * (APAGE * 128), &tm_k, &k_full[s],
-                        kvh * D + c * 64, pages[pg] * APAGE);
+        for (int c = 0; c < DB; ++c)
+          tma_load_2d(k_s + s * Cfg::kKVBytes + c * (BKV * 128), &tm_k, &k_full[s], kvh * D + c * 64, page * APAGE);
         mbar_wait(&v_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&v_full[s], Cfg::kKVBytes);
 #pragma unroll
-        for (int pg = 0; pg < PB; ++pg)
-#pragma unroll
-          for (int c = 0; c < DB; ++c)
-            tma_load_2d(v_s + s * Cfg::kKVBytes + c * (BKV * 128) + pg * (APAGE * 128), &tm_v, &v_full[s],
-                        kvh * D + c * 64, pages[pg] * APAGE);
+        for (int c = 0; c < DB; ++c)
+          tma_load_2d(v_s + s * Cfg::kKVBytes + c * (BKV * 128), &tm_v, &v_full[s], kvh * D + c * 64, page * APAGE);
       }
     }
   } else if (warp == 1) {
@@ -224,7 +244,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t a = make_sw128_kmajor_desc(smem_u32(p_s + (kk / 4) * (128 * 128))) + static_cast<uint64_t>((kk % 4) * 2);
+          const uint64_t a = make_sw128_kmajor_desc(smem_u32(p_s)) + static_cast<uint64_t>(kk * 2);
           const uint64_t b = make_sw128_mnmajor_desc(smem_u32(v_s + s * Cfg::kKVBytes + kk * (16 * 128)), BKV * 128);
           umma_bf16(tmem + O_COL, a, b, idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
         }
@@ -242,34 +262,33 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int qpos = pos0 + i;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const float cap = p.softcap;
-    float m_ref = -INFINITY, l = 0.f;
-
     const float inv_cap = SOFTCAP ? 1.f / cap : 0.f;
-    // raw score -> (soft-cap) -> log2 domain; MASKED tiles also apply the causal / window / length predicate
-    auto score = [&](float s, int kvpos, auto masked) {
-      if constexpr (SOFTCAP) s = cap * tanhf(s * inv_cap);
-      s *= LOG2E;
-      if constexpr (decltype(masked)::value) {
-        const bool ok = row_valid && kvpos <= qpos && kvpos < kvlen && (p.window <= 0 || kvpos > qpos - p.window);
-        return ok ? s : -INFINITY;
-      } else {
-        return s;
-      }
-    };
+    float m_ref = -INFINITY, l = 0.f;
 
     auto tile = [&](int n, auto masked) {
       const int t = t_lo + n, b = n & 1;
       mbar_wait(&s_full[b], static_cast<uint32_t>((n >> 1) & 1));
       tc_fence_after();
       const uint32_t s_addr = lane_addr + S_COL + static_cast<uint32_t>(b) * BKV;
-      // pass 1: row maximum (log2 domain)
+      // the whole score row of this tile lives in registers: one TMEM read, one wait
+      uint32_t r[BKV];
+      tmem_ld32_issue(s_addr, r);
+      tmem_ld32_issue(s_addr + 32, r + 32);
+      tmem_ld_fence(r);
+      tmem_ld_fence(r + 32);
       float mrow = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        float v[32];
-        tmem_ld32(s_addr + c, v);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mrow = fmaxf(mrow, score(v[e], t * BKV + c + e, masked));
+      for (int e = 0; e < BKV; ++e) {
+        float sc = __uint_as_float(r[e]);
+        if constexpr (SOFTCAP) sc = cap * tanhf(sc * inv_cap);
+        sc *= LOG2E;
+        if constexpr (decltype(masked)::value) {
+          const int kvpos = t * BKV + e;
+          const bool ok = row_valid && kvpos <= qpos && kvpos < kvlen && (p.window <= 0 || kvpos > qpos - p.window);
+          sc = ok ? sc : -INFINITY;
+        }
+        r[e] = __float_as_uint(sc);
+        mrow = fmaxf(mrow, sc);
       }
       // lazy rescaling: keep the reference max while the new maximum is within 2^8 of it
       float alpha = 1.f;
@@ -291,33 +310,24 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           }
         }
       }
-      l *= alpha;
-      // pass 2: P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile (A operand of the PV MMA)
+      // P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile (A operand of the PV MMA)
       const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;          // fully masked so far: exp2(-inf - 0) = 0
       float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        float v[32];
-        tmem_ld32(s_addr + c, v);
-        uint32_t packed[16];
+      uint8_t* ptile = p_s + row * 128;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = exp2f(score(v[e], t * BKV + c + e, masked) - mr);
-          const float p1 = exp2f(score(v[e + 1], t * BKV + c + e + 1, masked) - mr);
+      for (int j = 0; j < BKV / 8; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(__uint_as_float(r[8 * j + 2 * e]) - mr);
+          const float p1 = exp2f(__uint_as_float(r[8 * j + 2 * e + 1]) - mr);
+          lsum += p0 + p1;
           const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          lsum += __low2float(h) + __high2float(h);
-          packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        uint8_t* ptile = p_s + (c >> 6) * (128 * 128) + row * 128;
-        const int ch0 = (c & 63) >> 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = (ch0 + j) ^ (row & 7);
-          *reinterpret_cast<uint4*>(ptile + ch * 16) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
+        *reinterpret_cast<uint4*>(ptile + ((j ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l += lsum;
+      l = l * alpha + lsum;
       fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
@@ -367,32 +377,32 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem);
+    tmem_dealloc<TCOLS>(tmem);
   }
 }
 
-template <int D, int BKV, bool SOFTCAP>
+template <int D, bool SOFTCAP>
 int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
-              int seqs, int qblocks, cudaStream_t s) {
-  using Cfg = AtcCfg<D, BKV>;
+                  int seqs, int qblocks, cudaStream_t s) {
+  using Cfg = AtcCfg<D>;
   static bool set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D, BKV, SOFTCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D, SOFTCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     set[dev] = true;
   }
-  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, BKV, SOFTCAP>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
+  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, SOFTCAP>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
                                         Cfg::kSmemBytes, s, 1, tq, tk, tv, p, G, QB));
 }
 
-template <int D, int BKV>
+template <int D>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
               int seqs, int qblocks, cudaStream_t s) {
-  return p.softcap > 0.f ? launch_tc_cap<D, BKV, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
-                         : launch_tc_cap<D, BKV, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+  return p.softcap > 0.f ? launch_tc_cap<D, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
+                         : launch_tc_cap<D, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
 }
 
 }  // namespace
@@ -424,9 +434,9 @@ int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache,
   p.max_pages = max_pages; p.n_q = n_q; p.n_kv = n_kv; p.window = window; p.softcap = softcap;
   const int qblocks = (max_q + QB - 1) / QB;
   switch (head_dim) {
-    case 64: return launch_tc<64, 128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
-    case 128: return launch_tc<128, 128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
-    case 256: return launch_tc<256, 64>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 64: return launch_tc<64>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 128: return launch_tc<128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 256: return launch_tc<256>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
     default: return -3;
   }
 }
