@@ -80,6 +80,12 @@ def build(verbose: bool = True, force: bool = False) -> Path:
         if force or not obj.exists():
             jobs.append((["g++", *cxx_flags, *inc, f"-I{CSRC}", "-c", str(s), "-o", str(obj)], None))
 
+    # drop objects of older source revisions (the cache is keyed by content hash)
+    keep = {o.name for o in objs}
+    for old in BUILD.glob("*.o"):
+        if old.name not in keep:
+            old.unlink(missing_ok=True)
+
     if jobs:
         if verbose:
             print(f"[bee2bee_b200] compiling {len(jobs)} translation unit(s) for sm_100a ...", flush=True)

@@ -116,6 +116,19 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t* r) {
                : "memory");
 }
 
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, rel. error 8.8e-5 << bf16 eps).
+// Kept for experiments: moving every other exponential here was SLOWER (660 vs 750 TFLOP/s at T=4096): the
+// softmax warps are issue/latency bound, not MUFU bound (profiles/attention_tc.md).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = __fadd_rd(x, 12582912.f);        // 1.5 * 2^23: floor(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);            // fractional part in [0, 1)
+  float p = fmaf(0.077119089663f, f, 0.227564394474f);
+  p = fmaf(p, f, 0.695146143436f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
 template <int D>
 struct AtcCfg {
   static constexpr int BKV = 64;                                  // keys per tile == one KV page
