@@ -127,12 +127,13 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
-         dbg: int = 0, w_scale: Optional[torch.Tensor] = None, streamk: Optional[bool] = None) -> Optional[torch.Tensor]:
+         dbg: int = 0, w_scale: Optional[torch.Tensor] = None, streamk: Optional[bool] = None,
+         sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
     if bn <= 0:
-        bn = pick_bn(m_tok)
+        bn = pick_bn_mx(m_tok) if sfa is not None else pick_bn(m_tok)
     if splitk <= 0:
         splitk = pick_splitk(n_out, m_tok, k, bn, epi)
     if epi == EPI_QKV_ROPE:
@@ -149,7 +150,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk)
+                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk, sfa, sfb)
     return out
 
 
@@ -171,6 +172,69 @@ def quant_fp8_rows(x: torch.Tensor, eps: float = 1e-5, with_rms: bool = False, o
         scale_out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
     native().quant_fp8_rows(x, out, scale_out, eps, with_rms)
     return out, scale_out
+
+
+# ------------------------------------------------------- MX (block-scaled) fp8
+MX_BLOCK = 32          # K elements per UE8M0 scale (OCP MX / tcgen05 kind::mxf8f6f4.block_scale)
+
+
+def pick_bn_mx(m_tok: int) -> int:
+    """token tile of an MX GEMM: the scale-factor chunks are laid out per tile of >= 32 rows"""
+    return max(32, pick_bn(m_tok))
+
+
+def mx_chunk_layout(sf: torch.Tensor, rows_per_tile: int = 128) -> torch.Tensor:
+    """[R, K/32] scale bytes (R multiple of 128, K multiple of 128) -> the tcgen05.cp chunk layout
+    [R/128][K/128][32 (r % 32)][4 (r / 32)][4 (k-block in chunk)] flattened (512 bytes per chunk)."""
+    R, nb = sf.shape
+    assert R % 128 == 0 and nb % 4 == 0
+    v = sf.view(R // 128, 4, 32, nb // 4, 4)              # tile, r/32, r%32, kchunk, j
+    return v.permute(0, 3, 2, 1, 4).contiguous().view(-1)
+
+
+def quantize_weight_mxfp8(w: torch.Tensor):
+    """[N, K] -> (e4m3 weights, UE8M0 scale factors in chunk layout).  W ~= q * 2^(sf - 127) per 32-K block."""
+    N, K = w.shape
+    assert N % 128 == 0 and K % 128 == 0, "MX weights: N and K must be multiples of 128"
+    blocks = w.float().view(N, K // MX_BLOCK, MX_BLOCK)
+    amax = blocks.abs().amax(dim=2)
+    mant, ex = torch.frexp(amax / 448.0)                   # amax/448 = mant * 2^ex, mant in [0.5, 1)
+    e = torch.where(mant > 0.5, ex, ex - 1).clamp(-126, 127)
+    e = torch.where(amax > 0, e, torch.full_like(e, -126))
+    q = (blocks * torch.exp2(-e.float())[:, :, None]).clamp(-448, 448).view(N, K).to(torch.float8_e4m3fn)
+    sf = (e + 127).to(torch.uint8)
+    return q.contiguous(), mx_chunk_layout(sf)
+
+
+def mx_dequant(q: torch.Tensor, sf_plain: torch.Tensor) -> torch.Tensor:
+    """reference helper: q [R, K] e4m3, sf_plain [R, K/32] uint8 -> fp32"""
+    R, K = q.shape
+    return (q.float().view(R, K // MX_BLOCK, MX_BLOCK) * torch.exp2(sf_plain.float() - 127.0)[:, :, None]).view(R, K)
+
+
+def mx_unchunk(sf_chunks: torch.Tensor, rows: int, K: int, bn: int = 128) -> torch.Tensor:
+    """inverse of the chunk layout for activations quantised with token tile ``bn``: -> [rows, K/32] uint8"""
+    nkc = K // 128
+    chunk = 1024 if bn > 128 else 512
+    tiles = (rows + bn - 1) // bn
+    v = sf_chunks[: tiles * nkc * chunk].view(tiles, nkc, chunk // 512, 32, 4, 4)      # tile, kc, half, r%32, r/32, j
+    v = v.permute(0, 2, 4, 3, 1, 5).contiguous().view(tiles, (chunk // 512) * 128, nkc * 4)   # tile, row in padded tile, kblock
+    return v[:, :bn].reshape(tiles * bn, nkc * 4)[:rows]
+
+
+def quant_mxfp8_rows(x: torch.Tensor, bn: int = 0, eps: float = 1e-5, with_rms: bool = False, out=None, sf_out=None):
+    """Dynamic MX quantisation of GEMM activations (optionally fused with the RMSNorm 1/rms scale);
+    returns (q, sf_chunks) for a GEMM whose token tile is ``bn`` (default: what ``gemm`` would pick)."""
+    T, K = x.shape
+    if bn <= 0:
+        bn = pick_bn_mx(T)
+    tiles = (T + bn - 1) // bn
+    if out is None:
+        out = torch.empty((T, K), device=x.device, dtype=torch.float8_e4m3fn)
+    if sf_out is None:
+        sf_out = torch.empty(tiles * (K // 128) * (1024 if bn > 128 else 512), device=x.device, dtype=torch.uint8)
+    native().quant_mxfp8_rows(x, out, sf_out, bn, eps, with_rms)
+    return out, sf_out
 
 
 # ----------------------------------------------------------------- elementwise

@@ -45,12 +45,24 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, double rope_theta, double q_scale,
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
-          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale, bool streamk) {
+          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale, bool streamk,
+          const OptT& sfa, const OptT& sfb) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
                 x.is_contiguous(), "fp8 gemm: w and x must be contiguous CUDA float8_e4m3fn");
-    TORCH_CHECK(w_scale.has_value() && w_scale->scalar_type() == at::kFloat, "fp8 gemm needs per-row w_scale (fp32)");
+    const bool mx = sfa.has_value();
+    TORCH_CHECK(mx == sfb.has_value(), "MX fp8 gemm needs both sfa and sfb");
+    if (mx) {
+      const int64_t nkc = w.size(1) / 128, chunk = bn > 128 ? 1024 : 512;
+      TORCH_CHECK(w.size(1) % 128 == 0 && bn >= 32, "MX fp8 gemm: K must be a multiple of 128 and bn >= 32");
+      TORCH_CHECK(sfa->scalar_type() == at::kByte && sfa->is_contiguous() && sfa->numel() >= (w.size(0) / 128) * nkc * 512,
+                  "MX fp8 gemm: sfa too small");
+      TORCH_CHECK(sfb->scalar_type() == at::kByte && sfb->is_contiguous() &&
+                      sfb->numel() >= ((x.size(0) + bn - 1) / bn) * nkc * chunk, "MX fp8 gemm: sfb too small");
+    } else {
+      TORCH_CHECK(w_scale.has_value() && w_scale->scalar_type() == at::kFloat, "fp8 gemm needs per-row w_scale (fp32)");
+    }
   } else {
     check_bf16(w, "w");
     check_bf16(x, "x");
@@ -67,6 +79,8 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.act_gelu = act_gelu ? 1 : 0;
   p.fp8 = fp8 ? 1 : 0;
   p.w_scale = ptr_or_null<const float>(w_scale);
+  p.sfa = fp8 ? ptr_or_null<const uint8_t>(sfa) : nullptr;
+  p.sfb = fp8 ? ptr_or_null<const uint8_t>(sfb) : nullptr;
   p.out = as_ptr<void>(out_ptr);
   p.ld_out = static_cast<int>(ld_out);
   p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
@@ -104,7 +118,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   }
   if (p.epi == b2b::EPI_RESIDUAL) TORCH_CHECK(p.residual != nullptr, "residual epilogue needs residual");
   if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
-  if (streamk && bn <= 64 && p.dbg == nullptr) {
+  if (streamk && bn <= 64 && p.dbg == nullptr && p.sfa == nullptr) {
     const int r = b2b::launch_gemm_sk(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream());
     if (r != -5) {
       check(r, "gemm_sk");
@@ -190,6 +204,19 @@ void quant_fp8_rows(const Tensor& x, const Tensor& q, const Tensor& scale_out, d
                                    static_cast<int>(x.numel() / h), h, static_cast<float>(eps), with_rms ? 1 : 0,
                                    cur_stream()),
         "quant_fp8_rows");
+}
+
+void quant_mxfp8_rows(const Tensor& x, const Tensor& q, const Tensor& sf, int64_t bn, double eps, bool with_rms) {
+  check_bf16(x, "x");
+  TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn && q.is_contiguous() && sf.scalar_type() == at::kByte &&
+                  sf.is_contiguous(), "quant_mxfp8_rows: q must be float8_e4m3fn, sf uint8");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = static_cast<int>(x.size(-1));
+  const int tokens = static_cast<int>(x.numel() / h);
+  TORCH_CHECK(sf.numel() >= ((tokens + bn - 1) / bn) * (h / 128) * (bn > 128 ? 1024 : 512), "quant_mxfp8_rows: sf too small");
+  check(b2b::launch_quant_mxfp8_rows(x.data_ptr(), q.data_ptr(), sf.data_ptr(), tokens, h, static_cast<int>(bn),
+                                     static_cast<float>(eps), with_rms ? 1 : 0, cur_stream()),
+        "quant_mxfp8_rows");
 }
 
 void flag_wait(int64_t flag, int64_t epoch, int64_t delta) {
@@ -362,6 +389,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("kv_append", &kv_append);
   m.def("add", &add);
   m.def("quant_fp8_rows", &quant_fp8_rows);
+  m.def("quant_mxfp8_rows", &quant_mxfp8_rows);
   m.def("flag_wait", &flag_wait);
   m.def("flag_signal", &flag_signal);
   m.def("decode_advance", &decode_advance);

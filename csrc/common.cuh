@@ -143,6 +143,35 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// MX block-scaled fp8: e4m3 x e4m3 with one UE8M0 scale per 32 K elements; the scale factors live in
+// TMEM (4 columns per 128 rows x 4 k-blocks; the descriptor's sf-id fields pick the k-block byte).
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+// smem -> TMEM copy of 32 rows x 16 bytes, replicated into the four 32-lane subpartitions (scale factors).
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// un-swizzled K-major descriptor of a contiguous [32 rows][16 bytes] scale-factor chunk (8-row atoms 128 B apart)
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 32;               // SBO: next 8-row atom
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// 1D bulk copy global -> shared with mbarrier transaction accounting (size multiple of 16 bytes)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // tcgen05.commit: arrive on an mbarrier once all previously issued MMAs retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -187,6 +216,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
 // kind::f8f6f4 with e4m3 x e4m3 -> fp32 (format code 0 for both).
 __host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t m, uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// kind::mxf8f6f4.block_scale, e4m3 x e4m3, UE8M0 scales: [4,6) b_sf_id, [23] scale format E8M0, [29,31) a_sf_id
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(uint32_t m, uint32_t n) {
+  return ((n >> 3) << 17) | (1u << 23) | ((m >> 4) << 24);
 }
 
 // ------------------------------------------------------------ cluster / DSMEM

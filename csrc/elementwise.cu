@@ -226,6 +226,63 @@ __global__ void quant_fp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8
   }
 }
 
+// MX (block-scaled) e4m3 quantisation of GEMM activations: one UE8M0 scale (2^e) per 32 consecutive K
+// elements, q = x * rstd * 2^-e.  Scale bytes are written directly in the 512-byte chunk layout that
+// tcgen05.cp expects for a token tile of `bn` rows (see GemmParams::sfb).  One CTA per token; a warp
+// iteration covers 128 K elements (8 lanes x 4 elements = one 32-element block).  Padding rows of the last
+// tile get scale 2^0 (a 0xFF byte would be NaN).
+__global__ void quant_mxfp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                        uint8_t* __restrict__ sf, int tokens, int h, int bn, float eps, int with_rms) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sh[32];
+  const int t = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int nkc = h / 128;
+  const int chunk_bytes = bn > 128 ? 1024 : 512;
+  const int tile = t / bn, n = t % bn, r = n & 127;
+  uint8_t* sfrow = sf + static_cast<size_t>(tile) * nkc * chunk_bytes + (n >> 7) * 512 + (r & 31) * 16 + (r >> 5) * 4;
+  if (t >= tokens) {
+    for (int i = threadIdx.x; i < nkc * 4; i += blockDim.x) sfrow[static_cast<size_t>(i >> 2) * chunk_bytes + (i & 3)] = 127;
+    return;
+  }
+  const uint2* row = reinterpret_cast<const uint2*>(x + static_cast<size_t>(t) * h);
+  float rs = 1.f;
+  if (with_rms) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < h / 4; i += blockDim.x) {
+      const uint2 v = row[i];
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+      ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    }
+    ss = block_sum(ss, sh);
+    rs = rsqrtf(ss / h + eps);
+  }
+  uint32_t* qrow = reinterpret_cast<uint32_t*>(q + static_cast<size_t>(t) * h);
+  for (int kc = warp; kc < nkc; kc += nw) {
+    const uint2 v = row[kc * 32 + lane];
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+    const float f0 = a.x * rs, f1 = a.y * rs, f2 = b.x * rs, f3 = b.y * rs;
+    float amax = fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3)));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    // e = ceil(log2(amax / 448)) clamped to the UE8M0 range; 2^e >= amax / 448 so |q| <= 448
+    const uint32_t u = __float_as_uint(amax * (1.f / 448.f));
+    int e = static_cast<int>(u >> 23) - 127 + ((u & 0x7FFFFFu) ? 1 : 0);
+    e = max(-126, min(127, e));
+    const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);      // 2^-e (e = 127 -> 2^-127 denormal -> 0; unreachable for bf16 inputs)
+    uint8_t o8[4];
+    o8[0] = __nv_cvt_float_to_fp8(f0 * inv, __NV_SATFINITE, __NV_E4M3);
+    o8[1] = __nv_cvt_float_to_fp8(f1 * inv, __NV_SATFINITE, __NV_E4M3);
+    o8[2] = __nv_cvt_float_to_fp8(f2 * inv, __NV_SATFINITE, __NV_E4M3);
+    o8[3] = __nv_cvt_float_to_fp8(f3 * inv, __NV_SATFINITE, __NV_E4M3);
+    qrow[kc * 32 + lane] = *reinterpret_cast<uint32_t*>(o8);
+    if ((lane & 7) == 0) sfrow[static_cast<size_t>(kc) * chunk_bytes + (lane >> 3)] = static_cast<uint8_t>(e + 127);
+  }
+}
+
 // Stand-alone handoff primitives (used by the unfused / cudaMemcpyPeer comparator path)
 __global__ void flag_wait_kernel(const uint32_t* flag, const uint32_t* epoch, uint32_t delta) {
   pdl_launch_dependents();
@@ -327,6 +384,15 @@ int launch_quant_fp8_rows(const void* x, void* q, float* scale_out, int tokens, 
   if (h % 8) return -2;
   launch_kernel(quant_fp8_rows_kernel, dim3(tokens), dim3(h >= 4096 ? 512 : 256), 0, s, 1,
                 static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), scale_out, h, eps, with_rms);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_quant_mxfp8_rows(const void* x, void* q, void* sf, int tokens, int h, int bn, float eps, int with_rms,
+                            cudaStream_t s) {
+  if (h % 128 || bn < 32 || (bn & (bn - 1))) return -2;
+  const int padded = (tokens + bn - 1) / bn * bn;
+  launch_kernel(quant_mxfp8_rows_kernel, dim3(padded), dim3(h >= 4096 ? 512 : 256), 0, s, 1,
+                static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), tokens, h, bn, eps,
+                with_rms);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s) {

@@ -45,7 +45,14 @@ struct GemmCfg {
   static constexpr int kStages = (BN <= 32) ? 5 : (BN == 64 ? 4 : (BN == 128 ? 6 : 4));
   static constexpr int kStageBytes = A_STAGE_BYTES + BN * ROW_BYTES;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4;
+  // MX (block-scaled fp8): the UE8M0 scale factors of a stage (one 512-byte chunk per 128 rows x 128 K)
+  // are staged in smem next to the ring and copied to TMEM columns behind the accumulator.
+  static constexpr int kSfaBytes = 512;
+  static constexpr int kSfbBytes = BN > 128 ? 1024 : 512;
+  static constexpr int kSfBytes = kSfaBytes + kSfbBytes;
+  static constexpr int kSfCol = kTmemCols;                      // first scale-factor column (2 x 16 columns)
+  static constexpr int kTmemColsMx = BN <= 32 ? 64 : (BN == 64 ? 128 : (BN == 128 ? 256 : 512));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 + kStages * kSfBytes;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -68,13 +75,18 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN, int EPI, bool FP8>
+// QM: 0 = bf16, 1 = fp8 e4m3 with per-row / per-token fp32 scales, 2 = MX fp8 (e4m3 + UE8M0 scale per 32 K)
+template <int BN, int EPI, int QM>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                       const __grid_constant__ CUtensorMap tmap_x,
                                                       const GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool FP8 = QM != 0;
+  constexpr bool MX = QM == 2;
   constexpr int STAGES = Cfg::kStages;
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
+  constexpr uint32_t TX_BYTES = STAGE_BYTES + (MX ? Cfg::kSfBytes : 0);
+  constexpr uint32_t TCOLS = MX ? Cfg::kTmemColsMx : Cfg::kTmemCols;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,6 +95,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+  uint8_t* sf_s = smem + STAGES * STAGE_BYTES + 256 + BN * 4;     // [STAGES][kSfBytes]: SFA chunk, SFB chunk(s)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+    tmem_alloc<TCOLS>(tmem_ptr_s);
   }
   tc_fence_before();
   __syncthreads();
@@ -130,9 +143,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       // Weight tiles depend on no earlier kernel: fill the ring with them first, THEN wait for
       // the producer of the activations (previous kernel via PDL, upstream piece via its flag).
       const int npre = nkb < STAGES ? nkb : STAGES;
+      const uint8_t* sfa_g = MX ? p.sfa + (static_cast<size_t>(tile_n) * nkb_total + kb_begin) * Cfg::kSfaBytes : nullptr;
+      const uint8_t* sfb_g = MX ? p.sfb + (static_cast<size_t>(blockIdx.y) * nkb_total + kb_begin) * Cfg::kSfbBytes : nullptr;
       for (int i = 0; i < npre; ++i) {
-        mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[i], TX_BYTES);
         tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BKE, tile_n * BM, pol_w);
+        if constexpr (MX) bulk_load(sf_s + i * Cfg::kSfBytes, sfa_g + static_cast<size_t>(i) * Cfg::kSfaBytes, Cfg::kSfaBytes, &full_bar[i]);
       }
       pdl_wait();
       if (p.wait_flag != nullptr) {
@@ -143,6 +159,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       for (int i = 0; i < npre; ++i) {
         tma_load_2d_hint(smem + i * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[i], (kb_begin + i) * BKE, tok0,
                          pol_x);
+        if constexpr (MX)
+          bulk_load(sf_s + i * Cfg::kSfBytes + Cfg::kSfaBytes, sfb_g + static_cast<size_t>(i) * Cfg::kSfbBytes, Cfg::kSfbBytes, &full_bar[i]);
       }
       int kb = npre;
       B2B_DBG(2);
@@ -150,16 +168,20 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
         tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BKE,
                          tile_n * BM, pol_w);
         tma_load_2d_hint(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tmap_x, &full_bar[s],
                          (kb_begin + kb) * BKE, tok0, pol_x);
+        if constexpr (MX) {
+          bulk_load(sf_s + s * Cfg::kSfBytes, sfa_g + static_cast<size_t>(kb) * Cfg::kSfaBytes, Cfg::kSfaBytes, &full_bar[s]);
+          bulk_load(sf_s + s * Cfg::kSfBytes + Cfg::kSfaBytes, sfb_g + static_cast<size_t>(kb) * Cfg::kSfbBytes, Cfg::kSfbBytes, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = MX ? make_idesc_mxf8(BM, BN) : (FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN));
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
@@ -169,11 +191,25 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (kb == 0) B2B_DBG(3);
         const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES));
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES));
+        uint32_t sfa_t = 0, sfb_t = 0;
+        if constexpr (MX) {
+          // scale factors of this stage: smem -> TMEM (tcgen05.cp executes in issue order with the MMAs below);
+          // two column sets alternate so that the copy for stage kb+1 never races the MMAs of stage kb
+          sfa_t = tmem_base + Cfg::kSfCol + static_cast<uint32_t>(kb & 1) * 16;
+          sfb_t = sfa_t + 4;
+          const uint32_t sf_addr = smem_u32(sf_s + s * Cfg::kSfBytes);
+          tmem_cp_32x128b_warpx4(sfa_t, make_sf_desc(sf_addr));
+          tmem_cp_32x128b_warpx4(sfb_t, make_sf_desc(sf_addr + Cfg::kSfaBytes));
+          if constexpr (BN > 128) tmem_cp_32x128b_warpx4(sfb_t + 4, make_sf_desc(sf_addr + Cfg::kSfaBytes + 512));
+        }
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
           // one MMA consumes 32 bytes of K per row (16 bf16 / 32 e4m3): +2 in the (addr >> 4) field
-          if constexpr (FP8) umma_f8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if constexpr (MX)
+            umma_mxf8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29),
+                      (kb > 0 || k > 0) ? 1u : 0u, sfa_t, sfb_t);
+          else if constexpr (FP8) umma_f8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           else umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                    // frees the smem slot when the MMAs retire
@@ -405,7 +441,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<TCOLS>(tmem_base);
   }
   if (threadIdx.x == 0) B2B_DBG(7);
 }
@@ -459,17 +495,17 @@ int make_tmap_shared(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   return make_tmap(m, ptr, rows, cols, ld, box_rows, elt_bytes);
 }
 
-template <int BN, int EPI, bool FP8>
+template <int BN, int EPI, int QM>
 static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, QM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI, FP8>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
+  return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI, QM>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
                                         dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(p.splitk), tw, tx, p));
 }
 
@@ -479,7 +515,11 @@ template <int BN>
 static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
 #define B2B_EPI_CASE(E)                                                                              \
   case E:                                                                                            \
-    return p.fp8 ? launch_bn_epi<BN, E, true>(p, tw, tx, stream) : launch_bn_epi<BN, E, false>(p, tw, tx, stream);
+    if (p.fp8 && p.sfa != nullptr) {                                                                 \
+      if constexpr (BN >= 32) return launch_bn_epi<BN, E, 2>(p, tw, tx, stream);                     \
+      else return -7;   /* MX scale-factor chunks are laid out for token tiles of >= 32 */           \
+    }                                                                                                \
+    return p.fp8 ? launch_bn_epi<BN, E, 1>(p, tw, tx, stream) : launch_bn_epi<BN, E, 0>(p, tw, tx, stream);
   switch (p.epi) {
     B2B_EPI_CASE(EPI_PLAIN)
     B2B_EPI_CASE(EPI_RESIDUAL)
@@ -491,19 +531,24 @@ static int launch_bn(const GemmParams& p, const CUtensorMap& tw, const CUtensorM
 #undef B2B_EPI_CASE
 }
 
-template <int BN, int EPI, bool FP8>
+template <int BN, int EPI, int QM>
 static int set_attr_one() {
-  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return static_cast<int>(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, QM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                GemmCfg<BN>::kSmemBytes));
+}
+template <int BN, int EPI>
+static int set_attr_epi() {
+  int r = 0;
+  if ((r = set_attr_one<BN, EPI, 0>()) || (r = set_attr_one<BN, EPI, 1>())) return r;
+  if constexpr (BN >= 32) r = set_attr_one<BN, EPI, 2>();
+  return r;
 }
 template <int BN>
 static int set_attr_bn() {
   int r = 0;
-  if ((r = set_attr_one<BN, EPI_PLAIN, false>()) || (r = set_attr_one<BN, EPI_PLAIN, true>())) return r;
-  if ((r = set_attr_one<BN, EPI_RESIDUAL, false>()) || (r = set_attr_one<BN, EPI_RESIDUAL, true>())) return r;
-  if ((r = set_attr_one<BN, EPI_GLU, false>()) || (r = set_attr_one<BN, EPI_GLU, true>())) return r;
-  if ((r = set_attr_one<BN, EPI_QKV_ROPE, false>()) || (r = set_attr_one<BN, EPI_QKV_ROPE, true>())) return r;
-  if ((r = set_attr_one<BN, EPI_GELU, false>()) || (r = set_attr_one<BN, EPI_GELU, true>())) return r;
+  if ((r = set_attr_epi<BN, EPI_PLAIN>()) || (r = set_attr_epi<BN, EPI_RESIDUAL>()) || (r = set_attr_epi<BN, EPI_GLU>()) ||
+      (r = set_attr_epi<BN, EPI_QKV_ROPE>()) || (r = set_attr_epi<BN, EPI_GELU>()))
+    return r;
   return 0;
 }
 // Opt every instantiation into its dynamic shared memory size up front (so the first real

@@ -372,6 +372,43 @@ def test_gemm_fp8_w8a8(m, n, k, splitk):
     close(out, x.float() @ w.float().t(), rtol=6e-2, atol=6e-2)              # and close to the bf16 result
 
 
+@pytest.mark.parametrize("m,n,k,splitk,bn", [(1, 256, 256, 1, 0), (33, 256, 512, 1, 0), (128, 256, 384, 1, 0),
+                                              (200, 384, 1024, 2, 0), (300, 256, 512, 1, 256)])
+def test_gemm_mxfp8_block_scaled(m, n, k, splitk, bn):
+    """tcgen05 kind::mxf8f6f4.block_scale: e4m3 operands with one UE8M0 scale per 32 K elements (scales in TMEM)."""
+    w, x = bf(n, k, scale=0.05, seed=1), bf(m, k, scale=2.0, seed=2)
+    # block magnitudes spread over 2^-6..2^5 so that a wrong scale-factor address shows up as a large error
+    x = (x.float() * torch.exp2(torch.randint(-6, 6, (m, k // 32), device="cuda").float()).repeat_interleave(32, 1)).to(torch.bfloat16)
+    w = (w.float() * torch.exp2(torch.randint(-4, 4, (n, k // 32), device="cuda").float()).repeat_interleave(32, 1)).to(torch.bfloat16)
+    wq, sfa = ops.quantize_weight_mxfp8(w)
+    bn = bn or ops.pick_bn_mx(m)
+    xq, sfb = ops.quant_mxfp8_rows(x, bn)
+    xd = ops.mx_dequant(xq, ops.mx_unchunk(sfb, m, k, bn))
+    wd = ops.mx_dequant(wq, ops.mx_unchunk(sfa, n, k, 128))
+    # quantiser: per-block power-of-two scale, e4m3 rounding (3 mantissa bits; subnormals below amax * 2^-15)
+    amax = x.float().view(m, k // 32, 32).abs().amax(-1).repeat_interleave(32, 1)
+    assert ((xd - x.float()).abs() <= 0.0625 * x.float().abs() + 1e-3 * amax).all()
+    out = ops.gemm(wq, xq, sfa=sfa, sfb=sfb, splitk=splitk, bn=bn)
+    ref_q = xd @ wd.t()                                     # exact math on the quantised operands
+    scale = ref_q.abs().max().item()
+    assert (out.float() - ref_q).abs().max().item() <= 6e-3 * scale      # bf16 output rounding
+    ref = x.float() @ w.float().t()
+    assert (out.float() - ref).abs().max().item() <= 5e-2 * ref.abs().max().item()
+
+
+def test_gemm_mxfp8_fused_rmsnorm_glu():
+    h, f, m = 512, 256, 40
+    x, gamma = bf(m, h, scale=3.0), (1 + 0.1 * torch.randn(h, device="cuda")).to(torch.bfloat16)
+    wg, wu = bf(f, h, scale=0.05, seed=1), bf(f, h, scale=0.05, seed=2)
+    wgu = ops.fold_gamma(ops.glu_interleave_rows(wg, wu), gamma)
+    q, sfa = ops.quantize_weight_mxfp8(wgu)
+    xq, sfb = ops.quant_mxfp8_rows(x, eps=1e-5, with_rms=True)
+    hmid = ops.gemm(q, xq, epi=ops.EPI_GLU, sfa=sfa, sfb=sfb)
+    xn = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-5) * gamma.float()
+    ref = torch.nn.functional.silu(xn @ wg.float().t()) * (xn @ wu.float().t())
+    close(hmid, ref, rtol=8e-2, atol=8e-2)
+
+
 def test_gemm_fp8_fused_rmsnorm_glu_residual():
     h, f, m = 512, 256, 9
     x, gamma, res = bf(m, h, scale=3.0), (1 + 0.1 * torch.randn(h, device="cuda")).to(torch.bfloat16), bf(m, 256)
