@@ -71,8 +71,11 @@ class NativePiece:
         self.device = torch.device(device)
         self.max_tokens, self.max_seqs, self.num_pages = max_tokens, max_seqs, num_pages
         self.fused_norm = cfg.norm == "rms"
-        # W8A8 e4m3: per-output-row weight scales, per-token dynamic activation scales (Llama / Mistral graphs)
-        self.fp8 = quant == "fp8" and self.fused_norm and not cfg.post_norms and cfg.glu
+        # W8A8 e4m3 (Llama / Mistral graphs).  "fp8": per-output-row weight scales x per-token activation scales
+        # applied in the epilogue; "mxfp8": OCP-MX block scaling, one UE8M0 scale per 32 K elements on both
+        # operands, applied by the tensor core (tcgen05 kind::mxf8f6f4.block_scale).
+        self.fp8 = quant in ("fp8", "mxfp8") and self.fused_norm and not cfg.post_norms and cfg.glu
+        self.mx = self.fp8 and quant == "mxfp8"
         self.wscale: Dict[str, torch.Tensor] = {}
         c = cfg
         assert c.hidden_size % 128 == 0 or c.hidden_size % 64 == 0, "hidden must be a multiple of 64"
@@ -125,11 +128,16 @@ class NativePiece:
         if self.fp8:
             for name in list(self.w):
                 if name.split(".")[-1] in ("wqkv", "wo", "wgu", "w_down") or name == "lm_head":
-                    self.w[name], self.wscale[name] = ops.quantize_weight_fp8(self.w[name])
+                    quantize = ops.quantize_weight_mxfp8 if self.mx else ops.quantize_weight_fp8
+                    self.w[name], self.wscale[name] = quantize(self.w[name])
             widths = {cfg.hidden_size, cfg.q_dim, cfg.ffn_size}
-            self._qbuf = {k: torch.zeros((max(max_tokens, max_seqs), k), device=self.device, dtype=torch.float8_e4m3fn)
-                          for k in widths}
-            self._qscale = torch.zeros(max(max_tokens, max_seqs), device=self.device, dtype=torch.float32)
+            rows = max(max_tokens, max_seqs)
+            self._qbuf = {k: torch.zeros((rows, k), device=self.device, dtype=torch.float8_e4m3fn) for k in widths}
+            self._qscale = torch.zeros(rows, device=self.device, dtype=torch.float32)
+            if self.mx:
+                # activation scale-factor chunks: worst case is 32-row tiles (512 B per tile and 128 K)
+                tiles = (rows + 31) // 32
+                self._qsf = {k: torch.zeros(tiles * (k // 128) * 512, device=self.device, dtype=torch.uint8) for k in widths}
 
         # ---- KV cache: one [pages, 64, n_kv, D] pair per layer
         self.k_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
@@ -158,9 +166,19 @@ class NativePiece:
 
     # ------------------------------------------------------------------ helpers
     def _quant(self, x: torch.Tensor, with_rms: bool):
-        """bf16 rows -> (e4m3 rows, per-token scale [x 1/rms]) in the preallocated staging buffers"""
+        """bf16 rows -> (e4m3 rows, activation-side gemm kwargs) in the preallocated staging buffers.
+        fp8: per-token scale [x 1/rms] rides in ``rstd``; mxfp8: 1/rms is folded into the quantised values and the
+        UE8M0 scale-factor chunks go to ``sfb``."""
         T, K = x.shape
-        return ops.quant_fp8_rows(x, self.cfg.norm_eps, with_rms, out=self._qbuf[K][:T], scale_out=self._qscale[:T])
+        if self.mx:
+            xq, sfb = ops.quant_mxfp8_rows(x, 0, self.cfg.norm_eps, with_rms, out=self._qbuf[K][:T], sf_out=self._qsf[K])
+            return xq, {"sfb": sfb}
+        xq, xs = ops.quant_fp8_rows(x, self.cfg.norm_eps, with_rms, out=self._qbuf[K][:T], scale_out=self._qscale[:T])
+        return xq, {"rstd": xs}
+
+    def _wkw(self, name: str) -> dict:
+        """weight-side gemm kwargs of a quantised weight"""
+        return {"sfa": self.wscale[name]} if self.mx else {"w_scale": self.wscale[name]}
 
     def weight_bytes(self) -> int:
         return sum(v.numel() * v.element_size() for v in self.w.values())
@@ -209,8 +227,8 @@ class NativePiece:
                 if self.fp8:
                     if li == 0 and wait_flag and inline:
                         ops.native().flag_wait(wait_flag, wait_epoch, 1)     # the quant kernel reads x first
-                    xq, xs = self._quant(x, with_rms=True)
-                    ops.gemm(self.w[p + "wqkv"], xq, rstd=xs, w_scale=self.wscale[p + "wqkv"], **qkv_kw)
+                    xq, akw = self._quant(x, with_rms=True)
+                    ops.gemm(self.w[p + "wqkv"], xq, **akw, **self._wkw(p + "wqkv"), **qkv_kw)
                 else:
                     r = None if inline else ops.rstd(x, eps)
                     ops.gemm(self.w[p + "wqkv"], x, rstd=r, norm_from_x=inline,
@@ -230,9 +248,8 @@ class NativePiece:
                 o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
                 ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
             elif self.fp8:
-                aq, asc = self._quant(a, with_rms=False)
-                ops.gemm(self.w[p + "wo"], aq, out=x2, epi=ops.EPI_RESIDUAL, residual=x, rstd=asc,
-                         w_scale=self.wscale[p + "wo"])
+                aq, akw = self._quant(a, with_rms=False)
+                ops.gemm(self.w[p + "wo"], aq, out=x2, epi=ops.EPI_RESIDUAL, residual=x, **akw, **self._wkw(p + "wo"))
             else:
                 ops.gemm(self.w[p + "wo"], a, out=x2, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"))
             # ---------------- MLP block
@@ -244,9 +261,9 @@ class NativePiece:
             elif is_tail and out_x is not None:
                 tail_kw = dict(out_ptr=out_x.data_ptr(), ld_out=c.hidden_size)
             if c.glu and self.fp8:
-                x2q, x2s = self._quant(x2, with_rms=True)
-                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=self.h_buf[:T], epi=ops.EPI_GLU, rstd=x2s,
-                                w_scale=self.wscale[p + "wgu"], act_gelu=(c.act == "gelu_tanh"))
+                x2q, akw = self._quant(x2, with_rms=True)
+                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=self.h_buf[:T], epi=ops.EPI_GLU, **akw,
+                                **self._wkw(p + "wgu"), act_gelu=(c.act == "gelu_tanh"))
             elif c.glu:
                 r2 = None
                 if self.fused_norm and not inline:
@@ -271,9 +288,9 @@ class NativePiece:
                     xn = tgt
             else:
                 if self.fp8:
-                    hq, hs = self._quant(hmid, with_rms=False)
+                    hq, akw = self._quant(hmid, with_rms=False)
                     ops.gemm(self.w[p + "w_down"], hq, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
-                             residual=x2, rstd=hs, w_scale=self.wscale[p + "w_down"], **tail_kw)
+                             residual=x2, **akw, **self._wkw(p + "w_down"), **tail_kw)
                 else:
                     ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
                              residual=x2, bias=self.w.get(p + "b_down"), **tail_kw)
@@ -293,9 +310,9 @@ class NativePiece:
             # the head GEMM of this piece consumed the input slot; release it to the upstream piece
             ops.native().flag_signal(0, 0, hand.in_epoch, hand.up_ack)
         if self.fused_norm and self.fp8 and "lm_head" in self.wscale:
-            lq, lsc = self._quant(xl, with_rms=True)
-            ops.gemm(self.w["lm_head"], lq, out=self.logits[:S], epi=ops.EPI_PLAIN, rstd=lsc,
-                     w_scale=self.wscale["lm_head"], out_fp32=True, bn=ops.pick_bn(S))
+            lq, akw = self._quant(xl, with_rms=True)
+            ops.gemm(self.w["lm_head"], lq, out=self.logits[:S], epi=ops.EPI_PLAIN, **akw, **self._wkw("lm_head"),
+                     out_fp32=True)
         elif self.fused_norm:
             ops.gemm(self.w["lm_head"], xl, out=self.logits[:S], epi=ops.EPI_PLAIN, norm_from_x=True, eps=eps,
                      out_fp32=True, bn=ops.pick_bn(S))

@@ -41,7 +41,9 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=0, help="micro-batch groups in flight (default: N)")
     ap.add_argument("--prompt-len", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="fp8 = W8A8 e4m3 GEMMs (secondary config)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8", "mxfp8"],
+                    help="fp8 = W8A8 e4m3 GEMMs with per-row/per-token scales; mxfp8 = block-scaled (UE8M0 per 32 K) "
+                         "tcgen05 kind::mxf8f6f4 GEMMs (secondary configs)")
     return ap.parse_args()
 
 
@@ -214,7 +216,8 @@ def run_ours(args):
         out = {"metric": "decode_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
                "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": (tok_s / base) if base else None,
-               "dtype": "bf16" if args.dtype == "bf16" else "fp8-e4m3 W8A8 (bf16 KV/attention/residual)",
+               "dtype": {"bf16": "bf16", "fp8": "fp8-e4m3 W8A8 per-row/per-token scales (bf16 KV/attention/residual)",
+                         "mxfp8": "mxfp8 block-scaled e4m3 W8A8, UE8M0 per 32 K (bf16 KV/attention/residual)"}[args.dtype],
                "data": "synthetic", "impl": "ours",
                "config": {"model": args.model, "global_batch": total, "seq_len": P + W + K, "prompt_len": P,
                           "parallelism": f"pp{world}", "pieces": world, "micro_batch_groups": groups,

@@ -393,7 +393,7 @@ def test_gemm_mxfp8_block_scaled(m, n, k, splitk, bn):
     scale = ref_q.abs().max().item()
     assert (out.float() - ref_q).abs().max().item() <= 6e-3 * scale      # bf16 output rounding
     ref = x.float() @ w.float().t()
-    assert (out.float() - ref).abs().max().item() <= 5e-2 * ref.abs().max().item()
+    assert ((out.float() - ref).norm() / ref.norm()).item() <= 0.08          # e4m3 noise vs the unquantised product
 
 
 def test_gemm_mxfp8_fused_rmsnorm_glu():

@@ -86,13 +86,15 @@ def test_engine_gpu_continuous_batching():
     eng2.close()
 
 
+@pytest.mark.parametrize("quant", ["fp8", "mxfp8"])
 @pytest.mark.parametrize("name", ["tiny-llama", "tiny-mistral"])
-def test_piece_fp8_close_to_oracle(name):
-    """W8A8 e4m3 GEMMs (per-row weight / per-token activation scales): logits stay within fp8 noise of the oracle."""
+def test_piece_fp8_close_to_oracle(name, quant):
+    """W8A8 e4m3 GEMMs (per-row/per-token scales, or MX block scaling): logits stay within fp8 noise of the oracle."""
     cfg = resolve_config(name)
     runner = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=4, groups=1, max_seq_len=256,
-                       max_prefill_tokens=128, seed=0, quant="fp8")
+                       max_prefill_tokens=128, seed=0, quant=quant)
     assert runner.piece.fp8 and runner.piece.w["l0.wqkv"].dtype == torch.float8_e4m3fn
+    assert runner.piece.mx == (quant == "mxfp8")
     oracle = _oracle(cfg)
     V = cfg.vocab_size
     prompts = [list(range(5, 45)), [7, 3, 9]]
