@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .. import ops
-from ..models.config import ModelConfig, balanced_split, split_layers
+from ..models.config import ModelConfig, balanced_split, piece_units, split_layers
 from ..models.native import BatchMeta, Handoff, NativePiece
 from ..models.weights import load_or_init
 from ..parallel.mesh import MeshComm
@@ -51,8 +51,14 @@ class GpuRunner:
         self.max_prefill_tokens = max_prefill_tokens
         self.hist_len = hist_len
         self.use_graphs = use_graphs
-        ranges = balanced_split(cfg, world)        # the last piece also streams the lm_head: give it fewer layers
-        self.layers = list(ranges[rank]) if rank < len(ranges) else []
+        # piece boundaries in half-layer units (attention block | MLP block), balanced for the wavefront: the last
+        # piece also streams the lm_head and runs the sampler.  B2B_UNIT_BOUNDS="0,3,8" overrides the search (tests).
+        env_bounds = os.environ.get("B2B_UNIT_BOUNDS", "")
+        bounds = [int(v) for v in env_bounds.split(",")] if env_bounds and world > 1 else None
+        self.unit_ranges = piece_units(cfg, world, bounds)
+        assert len(self.unit_ranges) == world, f"{cfg.name}: cannot split into {world} pieces ({self.unit_ranges})"
+        self.units = self.unit_ranges[rank]
+        self.layers = list(range(self.units[0] // 2, (self.units[1] + 1) // 2))
         self.first, self.last = rank == 0, rank == world - 1
         if num_pages <= 0:
             num_pages = 1 + max_batch * self.max_pages_per_seq
@@ -61,7 +67,7 @@ class GpuRunner:
                                dtype=torch.bfloat16, seed=seed)
         max_tokens = max(max_prefill_tokens, self.gb)
         self.piece = NativePiece(cfg, self.layers, self.first, self.last, tensors, self.device, max_tokens,
-                                 max(self.gb, 64), num_pages, quant=quant)
+                                 max(self.gb, 64), num_pages, quant=quant, units=self.units)
         del tensors
         self.mesh = MeshComm(rank, world, self.device, cfg.hidden_size, max_tokens, groups, self.gb, hist_len,
                              control_group)
@@ -115,6 +121,7 @@ class GpuRunner:
         else:
             per = 5
         total = 1 + n * per                      # decode_advance + layers
+        total -= (3 if self.piece.head_skip_attn else 0) + (2 if self.piece.tail_skip_mlp else 0)   # half-layer ends
         if self.first:
             total += 1                           # embed
         if self.last:

@@ -66,8 +66,21 @@ class BatchMeta:
 
 class NativePiece:
     def __init__(self, cfg: ModelConfig, layers: Iterable[int], first: bool, last: bool, tensors: Tensors,
-                 device: torch.device, max_tokens: int, max_seqs: int, num_pages: int, quant: str = "bf16"):
+                 device: torch.device, max_tokens: int, max_seqs: int, num_pages: int, quant: str = "bf16",
+                 units: Optional[tuple] = None):
+        # ``units`` = (u0, u1) in half-layer units (2l = attention block of layer l, 2l+1 = its MLP block); a piece
+        # may start at an MLP block (the upstream piece ran that layer's attention) and / or end after an
+        # attention block (config.piece_units).  Default: whole layers.
+        if units is not None:
+            layers = range(units[0] // 2, (units[1] + 1) // 2)
+            self.head_skip_attn, self.tail_skip_mlp = units[0] % 2 == 1, units[1] % 2 == 1
+        else:
+            self.head_skip_attn = self.tail_skip_mlp = False
         self.cfg, self.layers, self.first, self.last = cfg, list(layers), first, last
+        if self.head_skip_attn or self.tail_skip_mlp:
+            from .config import supports_half_layer_pieces
+            assert supports_half_layer_pieces(cfg), "half-layer piece boundaries need the fused RMSNorm / GLU graph"
+            assert not (self.tail_skip_mlp and last), "the last piece ends with a whole layer"
         self.device = torch.device(device)
         self.max_tokens, self.max_seqs, self.num_pages = max_tokens, max_seqs, num_pages
         self.fused_norm = cfg.norm == "rms"
@@ -85,6 +98,9 @@ class NativePiece:
         self.w: Dict[str, torch.Tensor] = {}
         for l in self.layers:
             p = f"l{l}."
+            if not self.has_attn(l):
+                self._load_mlp_only(t, p)
+                continue
             wq, wk, wv = t[p + "wq"], t[p + "wk"], t[p + "wv"]
             if c.rope_theta > 0:
                 wq = ops.rope_interleave_rows(wq, c.n_heads, c.head_dim)
@@ -94,6 +110,8 @@ class NativePiece:
                 wqkv = ops.fold_gamma(wqkv, t[p + "ln1_w"], c.gemma_norm)
             self.w[p + "wqkv"] = wqkv.contiguous()
             self.w[p + "wo"] = t[p + "wo"].contiguous()
+            if not self.has_mlp(l):
+                continue
             if c.glu:
                 wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
                 if self.fused_norm:
@@ -139,11 +157,11 @@ class NativePiece:
                 tiles = (rows + 31) // 32
                 self._qsf = {k: torch.zeros(tiles * (k // 128) * 512, device=self.device, dtype=torch.uint8) for k in widths}
 
-        # ---- KV cache: one [pages, 64, n_kv, D] pair per layer
+        # ---- KV cache: one [pages, 64, n_kv, D] pair per layer whose attention block runs on this piece
         self.k_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
-                        for l in self.layers}
+                        for l in self.layers if self.has_attn(l)}
         self.v_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
-                        for l in self.layers}
+                        for l in self.layers if self.has_attn(l)}
         # ---- activations
         H = c.hidden_size
         self.xa = torch.zeros((max_tokens, H), device=dev, dtype=bf)
@@ -165,6 +183,19 @@ class NativePiece:
                                    dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
+    def has_attn(self, l: int) -> bool:
+        return not (self.head_skip_attn and l == self.layers[0])
+
+    def has_mlp(self, l: int) -> bool:
+        return not (self.tail_skip_mlp and l == self.layers[-1])
+
+    def _load_mlp_only(self, t, p: str) -> None:
+        """first layer of a piece that starts at the MLP block (fused-norm GLU graphs only)"""
+        c = self.cfg
+        wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
+        self.w[p + "wgu"] = ops.fold_gamma(wgu, t[p + "ln2_w"], c.gemma_norm)
+        self.w[p + "w_down"] = t[p + "w_down"].contiguous()
+
     def _quant(self, x: torch.Tensor, with_rms: bool):
         """bf16 rows -> (e4m3 rows, activation-side gemm kwargs) in the preallocated staging buffers.
         fp8: per-token scale [x 1/rms] rides in ``rstd``; mxfp8: 1/rms is folded into the quantised values and the
@@ -211,48 +242,12 @@ class NativePiece:
         n_layers = len(self.layers)
         for li, l in enumerate(self.layers):
             p = f"l{l}."
+            do_attn, do_mlp = self.has_attn(l), self.has_mlp(l)
             is_tail = (li == n_layers - 1) and not self.last
+            head_wait = wait_flag if li == 0 else 0           # the piece's first GEMM consumes the handoff input
+            head_epoch = wait_epoch if li == 0 else 0
             x2 = self.xb[:T]
             xn = self.xa[:T]            # layer output buffer (local)
-            # ---------------- attention block
-            if self.fused_norm:
-                if li == 0 and wait_flag and not inline:
-                    # wide token tiles use a separate 1/rms kernel that reads the peer-written rows:
-                    # acquire the handoff flag first (the GEMM's own wait then passes immediately)
-                    ops.native().flag_wait(wait_flag, wait_epoch, 1)
-                qkv_kw = dict(epi=ops.EPI_QKV_ROPE, eps=eps, q_out=self.q_buf, k_cache=self.k_cache[l],
-                              v_cache=self.v_cache[l], positions=m.positions, slots=m.slots, n_q_heads=c.n_heads,
-                              n_kv_heads=c.n_kv_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
-                              q_scale=c.softmax_scale)
-                if self.fp8:
-                    if li == 0 and wait_flag and inline:
-                        ops.native().flag_wait(wait_flag, wait_epoch, 1)     # the quant kernel reads x first
-                    xq, akw = self._quant(x, with_rms=True)
-                    ops.gemm(self.w[p + "wqkv"], xq, **akw, **self._wkw(p + "wqkv"), **qkv_kw)
-                else:
-                    r = None if inline else ops.rstd(x, eps)
-                    ops.gemm(self.w[p + "wqkv"], x, rstd=r, norm_from_x=inline,
-                             wait_flag=wait_flag if li == 0 else 0, wait_epoch=wait_epoch if li == 0 else 0, **qkv_kw)
-            else:
-                if li == 0 and wait_flag:
-                    ops.native().flag_wait(wait_flag, wait_epoch, 1)
-                n = ops.layernorm(x, self.w[p + "ln1_w"], self.w[p + "ln1_b"], self.n_buf[:T], eps)
-                ops.gemm(self.w[p + "wqkv"], n, out=self.qkv_buf[:T], epi=ops.EPI_PLAIN, bias=self.w.get(p + "bqkv"))
-                ops.kv_append(self.qkv_buf[:T], self.q_buf, self.k_cache[l], self.v_cache[l], m.slots, c.q_dim,
-                              c.kv_dim, c.softmax_scale)
-            ops.attention(self.q_buf, self.k_cache[l], self.v_cache[l], self.attn_buf, m.block_table, m.q_start,
-                          m.q_len, m.kv_len, max_q=m.max_q, n_q=c.n_heads, n_kv=c.n_kv_heads, head_dim=c.head_dim,
-                          window=c.layer_window(l), softcap=c.attn_softcap, splits=m.splits, ws=self.attn_ws)
-            a = self.attn_buf[:T]
-            if c.post_norms:
-                o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
-                ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
-            elif self.fp8:
-                aq, akw = self._quant(a, with_rms=False)
-                ops.gemm(self.w[p + "wo"], aq, out=x2, epi=ops.EPI_RESIDUAL, residual=x, **akw, **self._wkw(p + "wo"))
-            else:
-                ops.gemm(self.w[p + "wo"], a, out=x2, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"))
-            # ---------------- MLP block
             tail_kw = {}
             if is_tail and hand.out_x:
                 tail_kw = dict(out_ptr=hand.out_x, ld_out=c.hidden_size, signal_flag=hand.out_flag,
@@ -260,6 +255,59 @@ class NativePiece:
                                bump_epoch=hand.in_epoch, ack_flag=hand.up_ack)
             elif is_tail and out_x is not None:
                 tail_kw = dict(out_ptr=out_x.data_ptr(), ld_out=c.hidden_size)
+            # ---------------- attention block
+            if not do_attn:
+                x2 = x                  # the upstream piece ran this layer's attention: x is the post-attention stream
+            elif self.fused_norm:
+                if head_wait and not inline:
+                    # wide token tiles use a separate 1/rms kernel that reads the peer-written rows:
+                    # acquire the handoff flag first (the GEMM's own wait then passes immediately)
+                    ops.native().flag_wait(head_wait, head_epoch, 1)
+                qkv_kw = dict(epi=ops.EPI_QKV_ROPE, eps=eps, q_out=self.q_buf, k_cache=self.k_cache[l],
+                              v_cache=self.v_cache[l], positions=m.positions, slots=m.slots, n_q_heads=c.n_heads,
+                              n_kv_heads=c.n_kv_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
+                              q_scale=c.softmax_scale)
+                if self.fp8:
+                    if head_wait and inline:
+                        ops.native().flag_wait(head_wait, head_epoch, 1)     # the quant kernel reads x first
+                    xq, akw = self._quant(x, with_rms=True)
+                    ops.gemm(self.w[p + "wqkv"], xq, **akw, **self._wkw(p + "wqkv"), **qkv_kw)
+                else:
+                    r = None if inline else ops.rstd(x, eps)
+                    ops.gemm(self.w[p + "wqkv"], x, rstd=r, norm_from_x=inline, wait_flag=head_wait,
+                             wait_epoch=head_epoch, **qkv_kw)
+            else:
+                if head_wait:
+                    ops.native().flag_wait(head_wait, head_epoch, 1)
+                n = ops.layernorm(x, self.w[p + "ln1_w"], self.w[p + "ln1_b"], self.n_buf[:T], eps)
+                ops.gemm(self.w[p + "wqkv"], n, out=self.qkv_buf[:T], epi=ops.EPI_PLAIN, bias=self.w.get(p + "bqkv"))
+                ops.kv_append(self.qkv_buf[:T], self.q_buf, self.k_cache[l], self.v_cache[l], m.slots, c.q_dim,
+                              c.kv_dim, c.softmax_scale)
+            if do_attn:
+                ops.attention(self.q_buf, self.k_cache[l], self.v_cache[l], self.attn_buf, m.block_table, m.q_start,
+                              m.q_len, m.kv_len, max_q=m.max_q, n_q=c.n_heads, n_kv=c.n_kv_heads, head_dim=c.head_dim,
+                              window=c.layer_window(l), softcap=c.attn_softcap, splits=m.splits, ws=self.attn_ws)
+                a = self.attn_buf[:T]
+                okw = {} if do_mlp else tail_kw          # piece ends after this attention block: O-proj is the tail GEMM
+                o_out = None if okw else x2
+                if c.post_norms:
+                    o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
+                    ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
+                elif self.fp8:
+                    aq, akw = self._quant(a, with_rms=False)
+                    ops.gemm(self.w[p + "wo"], aq, out=o_out, epi=ops.EPI_RESIDUAL, residual=x, **akw,
+                             **self._wkw(p + "wo"), **okw)
+                else:
+                    ops.gemm(self.w[p + "wo"], a, out=o_out, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"),
+                             **okw)
+                if not do_mlp:
+                    x = out_x[:T] if (okw and out_x is not None and not hand.out_x) else x2
+                    continue
+            # ---------------- MLP block
+            mlp_wait = head_wait if not do_attn else 0      # piece starts at this MLP block: gate/up consumes the input
+            mlp_epoch = head_epoch if not do_attn else 0
+            if mlp_wait and (self.fp8 or not inline):
+                ops.native().flag_wait(mlp_wait, mlp_epoch, 1)   # a separate quant / 1/rms kernel reads x2 first
             if c.glu and self.fp8:
                 x2q, akw = self._quant(x2, with_rms=True)
                 hmid = ops.gemm(self.w[p + "wgu"], x2q, out=self.h_buf[:T], epi=ops.EPI_GLU, **akw,
@@ -269,7 +317,8 @@ class NativePiece:
                 if self.fused_norm and not inline:
                     r2 = ops.rstd(x2, eps)
                 hmid = ops.gemm(self.w[p + "wgu"], x2, out=self.h_buf[:T], epi=ops.EPI_GLU, rstd=r2,
-                                norm_from_x=inline and self.fused_norm, eps=eps, act_gelu=(c.act == "gelu_tanh"))
+                                norm_from_x=inline and self.fused_norm, eps=eps, act_gelu=(c.act == "gelu_tanh"),
+                                wait_flag=mlp_wait, wait_epoch=mlp_epoch)
             else:
                 n2 = ops.layernorm(x2, self.w[p + "ln2_w"], self.w[p + "ln2_b"], self.n_buf[:T], eps)
                 hmid = ops.gemm(self.w[p + "w_up"], n2, out=self.h_buf[:T], epi=ops.EPI_GELU, bias=self.w.get(p + "b_up"))
@@ -287,6 +336,8 @@ class NativePiece:
                     ops.rmsnorm(d, self.w[p + "post_ffn_w"], out=tgt, residual=x2, eps=eps, plus_one=c.gemma_norm)
                     xn = tgt
             else:
+                if not do_attn and xn.data_ptr() == x2.data_ptr():
+                    xn = self.xb[:T]    # x2 aliases the input buffer here: keep the residual source intact
                 if self.fp8:
                     hq, akw = self._quant(hmid, with_rms=False)
                     ops.gemm(self.w[p + "w_down"], hq, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,

@@ -220,7 +220,9 @@ def run_ours(args):
                          "mxfp8": "mxfp8 block-scaled e4m3 W8A8, UE8M0 per 32 K (bf16 KV/attention/residual)"}[args.dtype],
                "data": "synthetic", "impl": "ours",
                "config": {"model": args.model, "global_batch": total, "seq_len": P + W + K, "prompt_len": P,
-                          "parallelism": f"pp{world}", "pieces": world, "micro_batch_groups": groups,
+                          "parallelism": f"pp{world}", "pieces": world,
+                          "piece_units": "/".join(str(b - a) for a, b in eng.runner.unit_ranges) + " half-layers",
+                          "micro_batch_groups": groups,
                           "batch_per_group": B, "weights": "random-init", "sampling": "T=0.7 top_p=0.95 rep=1.15",
                           "l2": "per-step weight stream (>=2 GB/GPU) exceeds the 126 MB L2; L2 flushed before timing"},
                "p50_ttft_ms": statistics.median(ttfts), "gpu_launches": launches, "clocks": clocks, "e2e": e2e,

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, model, groups, batch, port):
-    env = dict(os.environ, B2B_MODEL=model, B2B_GROUPS=str(groups), B2B_BATCH=str(batch), MASTER_ADDR="127.0.0.1")
+def _run(world, model, groups, batch, port, **extra_env):
+    env = dict(os.environ, B2B_MODEL=model, B2B_GROUPS=str(groups), B2B_BATCH=str(batch), MASTER_ADDR="127.0.0.1",
+               **extra_env)
     if world == 1:
         cmd = [sys.executable, os.path.join(ROOT, "tools", "mp_check.py")]
     else:
@@ -32,6 +33,16 @@ def test_two_gpu_pipeline_matches_single_gpu(model):
     # same total batch; 2 wavefront groups on the 2-rank mesh, and the same grouping on one rank
     ref = _run(1, model, 2, 4, 0)
     got = _run(2, model, 2, 4, 29611)
+    assert got == ref
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("bounds", ["0,3,8", "0,5,8"])
+def test_two_gpu_half_layer_piece_boundary(bounds):
+    """Piece boundary inside a layer: piece 0 ends with an attention block (O-proj is the fused tail GEMM that
+    stores into the peer), piece 1 starts at the MLP block (gate/up is the head GEMM that acquires the flag)."""
+    ref = _run(1, "tiny-llama", 2, 4, 0)
+    got = _run(2, "tiny-llama", 2, 4, 29617, B2B_UNIT_BOUNDS=bounds)
     assert got == ref
 
 
