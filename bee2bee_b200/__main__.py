@@ -163,6 +163,19 @@ def register(node_url, network, region, test):
     sys.exit(asyncio.run(_reg()))
 
 
+@cli.command()
+@click.option("--host", default="0.0.0.0", help="Bind host")
+@click.option("--port", default=None, type=int, help="HTTP port (default: $API_PORT or 3000)")
+@click.option("--seed", "seeds", multiple=True, help="Node address or join link to dial at start-up (repeatable; "
+              "default: $BEE2BEE_SEEDS)")
+def gateway(host, port, seeds):
+    """Web gateway: /api/p2p/{register,generate,status,global_metrics} + a minimal chat page
+    (the reference's Express app + bridge, app/api/index.js / bridge.js)."""
+    from .gateway import main as gateway_main
+
+    gateway_main(host=host, port=port, seeds=list(seeds) or None)
+
+
 @cli.command("config")
 @click.argument("key", required=False)
 @click.argument("value", required=False)
