@@ -52,7 +52,7 @@ struct GemmCfg {
   static constexpr int kSfBytes = kSfaBytes + kSfbBytes;
   static constexpr int kSfCol = kTmemCols;                      // first scale-factor column (2 x 16 columns)
   static constexpr int kTmemColsMx = BN <= 32 ? 64 : (BN == 64 ? 128 : (BN == 128 ? 256 : 512));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 + kStages * kSfBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 12 + kStages * kSfBytes;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
-  uint8_t* sf_s = smem + STAGES * STAGE_BYTES + 256 + BN * 4;     // [STAGES][kSfBytes]: SFA chunk, SFB chunk(s)
+  int* pos_s = reinterpret_cast<int*>(rstd_s + BN);               // [BN] token positions (QKV/RoPE epilogue)
+  int* slot_s = pos_s + BN;                                       // [BN] KV-cache slots
+  uint8_t* sf_s = smem + STAGES * STAGE_BYTES + 256 + BN * 12;    // [STAGES][kSfBytes]: SFA chunk, SFB chunk(s)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,6 +224,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const int et = threadIdx.x - 64;   // 0..127
     pdl_wait();                        // everything below reads / writes memory of earlier kernels
     if (leader) {
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        // per-token metadata -> smem once: global loads inside the store loop of the epilogue serialise on L2
+        // latency (the compiler cannot hoist them above stores that may alias): +8 us at 32 tokens
+        for (int t = et; t < BN; t += 128) {
+          const int tok = tok0 + t;
+          pos_s[t] = (p.positions != nullptr && tok < p.m_tok) ? p.positions[tok] : 0;
+          slot_s[t] = (tok < p.m_tok) ? p.slots[tok] : -1;
+        }
+      }
       if (p.norm_src != nullptr) {
         if (p.wait_flag != nullptr) {
           const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
@@ -240,19 +251,25 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             live[u] = (t + 4 * u < BN) && tok < p.m_tok;
             rowp[u] = reinterpret_cast<const uint4*>(p.norm_src + static_cast<size_t>(live[u] ? tok : tok0) * p.k);
           }
-          for (int i = lane; i < kv8; i += 32) {
-            uint4 v[4];
+          // 4 tokens x 4 row segments = 16 independent 128-bit loads per lane before the first use
+          for (int i0 = lane; i0 < kv8; i0 += 128) {
+            uint4 v[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = live[u] ? rowp[u][i] : make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+              for (int u = 0; u < 4; ++u)
+                v[j][u] = (live[u] && i0 + 32 * j < kv8) ? rowp[u][i0 + 32 * j] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __bfloat1622float2(h[j]);
-                ss[u] += f.x * f.x + f.y * f.y;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[j][u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  ss[u] += f.x * f.x + f.y * f.y;
+                }
               }
-            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -359,6 +376,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     for (int c = 0; c < BN; c += 16) {
       if (EPI == EPI_GLU && row >= 64) break;
       if (tok0 + c >= p.m_tok) break;
+      // residual values of the whole chunk first: 16 independent loads in flight (one L2 round trip) instead of
+      // one per token between dependent stores
+      __nv_bfloat16 resid[16];
+      if constexpr (EPI == EPI_RESIDUAL) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int tok = tok0 + c + i;
+          resid[i] = (tok < p.m_tok) ? p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob] : __float2bfloat16_rn(0.f);
+        }
+      }
       float v[16];
       tmem_ld16(taddr + c, v);
       for (int r = 0; r < splitk - 1; ++r) {
@@ -383,9 +410,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
               __float2bfloat16_rn(gelu_tanh(a));
         } else if constexpr (EPI == EPI_RESIDUAL) {
-          const float r = __bfloat162float(p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob]);
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
-              __float2bfloat16_rn(a + r);
+              __float2bfloat16_rn(a + __bfloat162float(resid[i]));
         } else if constexpr (EPI == EPI_GLU) {
           const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
@@ -397,13 +423,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             // lanes (2j, 2j+1) hold (x_j, x_{j+hd/2}) thanks to the offline row interleave
             const float partner = __shfl_xor_sync(0xffffffffu, a, 1);
             float sn, cs;
-            sincosf(static_cast<float>(p.positions[tok]) * inv_freq, &sn, &cs);
+            sincosf(static_cast<float>(pos_s[c + i]) * inv_freq, &sn, &cs);
             o = (lane & 1) ? (a * cs + partner * sn) : (a * cs - partner * sn);
           }
           if (sect == 0) {
             p.q_out[static_cast<size_t>(tok) * q_dim + f_in_sect] = __float2bfloat16_rn(o * p.q_scale);
           } else {
-            const int slot = p.slots[tok];
+            const int slot = slot_s[c + i];
             __nv_bfloat16* dst = (sect == 1 ? p.k_cache : p.v_cache);
             if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
           }

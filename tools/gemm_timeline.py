@@ -6,7 +6,10 @@ from bee2bee_b200 import ops
 C = ops.native(); C.init_kernels(0)
 names = ["entry", "setup_done", "prefetch_issued", "first_full", "last_mma_commit", "tmem_full_seen", "epi_done", "exit"]
 flush = torch.empty(300 << 20, dtype=torch.uint8, device="cuda")
-for (m, n, k, sk) in [(32, 4096, 4096, 1), (32, 4096, 4096, 4), (32, 28672, 4096, 1), (32, 4096, 14336, 4)]:
+shapes = [(32, 4096, 4096, 1), (32, 4096, 4096, 4), (32, 28672, 4096, 1), (32, 4096, 14336, 4)]
+if os.environ.get('TL_M'):
+    shapes = [(int(m), n, k, sk) for m in os.environ['TL_M'].split(',') for (n, k, sk) in [(4096, 4096, 4), (6144, 4096, 2), (4096, 4096, 1)]]
+for (m, n, k, sk) in shapes:
     w = (torch.randn(n, k, device="cuda") * 0.02).bfloat16(); x = torch.randn(m, k, device="cuda").bfloat16()
     out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
     nct = (n // 128) * sk
