@@ -192,9 +192,8 @@ class GpuRunner:
     PF_BUCKETS = (16, 32, 64)
 
     def _prefill_graph_ok(self, seqs) -> bool:
-        # experimental (off by default): replays after the capturing call produce wrong attention outputs on
-        # B200 although q/K/V match -- see DESIGN.md known gaps; eager prefill is the validated path
-        return (os.environ.get("B2B_PREFILL_GRAPH", "0") == "1" and self.use_graphs and self.world == 1
+        # single short prompt (the chat / TTFT case): one H2D copy + one graph replay; B2B_PREFILL_GRAPH=0 disables
+        return (os.environ.get("B2B_PREFILL_GRAPH", "1") == "1" and self.use_graphs and self.world == 1
                 and len(seqs) == 1 and 0 < len(seqs[0].prompt) <= self.PF_BUCKETS[-1]
                 and self.max_prefill_tokens >= self.PF_BUCKETS[-1])
 
@@ -214,7 +213,9 @@ class GpuRunner:
         bt = stage[3 * tb + 8:3 * tb + 8 + mp].view(1, mp)              # this sequence's block-table row
         qstart = torch.zeros(1, device=dev, dtype=i32)
         last64 = torch.zeros(1, device=dev, dtype=torch.int64)
-        st = {"host": host, "stage": stage, "graph": None}
+        # the captured kernels address these tensors by raw pointer: they must outlive this function (qstart / last64
+        # used to be locals of the capture closure -> freed, reallocated, and the replays read garbage offsets)
+        st = {"host": host, "stage": stage, "graph": None, "keep": (qstart, last64)}
 
         def body():
             # no torch gather/scatter ops in here: every per-sequence input is either staged by the single

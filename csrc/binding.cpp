@@ -245,7 +245,7 @@ void flag_signal(int64_t flag, int64_t epoch, int64_t bump_epoch, int64_t ack_fl
 // query-chunk length from which the tensor-core prefill kernel is used (0 = never); env B2B_ATTN_TC_MIN_Q
 static int64_t g_attn_tc_min_q = [] {
   const char* e = std::getenv("B2B_ATTN_TC_MIN_Q");
-  return e ? static_cast<int64_t>(std::atoi(e)) : static_cast<int64_t>(16);
+  return e ? static_cast<int64_t>(std::atoi(e)) : static_cast<int64_t>(2);
 }();
 void set_attn_tc_min_q(int64_t v) { g_attn_tc_min_q = v; }
 int64_t get_attn_tc_min_q() { return g_attn_tc_min_q; }

@@ -121,7 +121,6 @@ def test_piece_fp8_close_to_oracle(name, quant):
     runner.close()
 
 
-@pytest.mark.skip(reason="graph-captured prefill is experimental and gated off (B2B_PREFILL_GRAPH=1)")
 def test_graph_prefill_matches_eager_prefill():
     """Single short prompts take the CUDA-graph prefill path (TTFT); results equal the eager chunked path."""
     cfg = resolve_config("tiny-llama")
