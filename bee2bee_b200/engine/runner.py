@@ -138,20 +138,30 @@ class GpuRunner:
             return
         dev, i32 = self.device, torch.int32
         with torch.cuda.stream(self.stream):
-            for s in seqs:
-                b = s.slot
-                row = torch.zeros(self.max_pages_per_seq, dtype=i32)
-                row[:len(s.pages)] = torch.tensor(s.pages, dtype=i32)
-                self.block_table[b].copy_(row.to(dev, non_blocking=True))
-                self.temperature[b] = s.temperature
-                self.top_p[b] = s.top_p
-                self.rep_pen[b] = s.repetition_penalty
-                self.seeds[b] = int(s.seed) & 0x7FFFFFFF
-                self.hist_pos[b] = 0
-                self.seen[b].zero_()
-                if self.last:
-                    ids = torch.tensor(s.prompt, dtype=i32, device=dev)
-                    ops.mark_seen(ids, torch.full_like(ids, b), self.seen, self.cfg.vocab_size)
+            # per-sequence state of all admitted sequences in a handful of batched copies (one tiny launch per
+            # field and sequence cost ~25 ms for 256 admissions)
+            S = len(seqs)
+            bt_host = torch.zeros((S, self.max_pages_per_seq), dtype=i32)
+            for i, s in enumerate(seqs):
+                bt_host[i, :len(s.pages)] = torch.tensor(s.pages, dtype=i32)
+            fl_host = torch.tensor([[s.temperature, s.top_p, s.repetition_penalty] for s in seqs], dtype=torch.float32)
+            seed_host = torch.tensor([int(s.seed) & 0x7FFFFFFF for s in seqs], dtype=i32)
+            rows = torch.tensor([s.slot for s in seqs], dtype=torch.int64).to(dev, non_blocking=True)
+            fl = fl_host.to(dev, non_blocking=True)
+            self.block_table.index_copy_(0, rows, bt_host.to(dev, non_blocking=True))
+            self.temperature.index_copy_(0, rows, fl[:, 0].contiguous())
+            self.top_p.index_copy_(0, rows, fl[:, 1].contiguous())
+            self.rep_pen.index_copy_(0, rows, fl[:, 2].contiguous())
+            self.seeds.index_copy_(0, rows, seed_host.to(dev, non_blocking=True))
+            self.hist_pos.index_fill_(0, rows, 0)
+            self.seen.index_fill_(0, rows, 0)
+            self.h2d_bytes += bt_host.numel() * 4 + fl_host.numel() * 4 + S * (4 + 8)
+            if self.last:
+                flat = [t for s in seqs for t in s.prompt]
+                self.h2d_bytes += 8 * len(flat)
+                owner = [s.slot for s in seqs for _ in s.prompt]
+                ops.mark_seen(torch.tensor(flat, dtype=i32).to(dev, non_blocking=True),
+                              torch.tensor(owner, dtype=i32).to(dev, non_blocking=True), self.seen, self.cfg.vocab_size)
             if self._prefill_graph_ok(seqs):
                 self._prefill_single_graph(seqs[0])
                 self.stream.synchronize()
@@ -180,11 +190,10 @@ class GpuRunner:
                 if self.world > 1:
                     self.stream.synchronize()
                     self.mesh.barrier()
-            for s in seqs:
-                b, L = s.slot, len(s.prompt)
-                self.positions[b] = L - 1
-                self.kv_len[b] = L
-                self.q_len[b] = 1
+            lens = torch.tensor([len(s.prompt) for s in seqs], dtype=i32).to(dev, non_blocking=True)
+            self.positions.index_copy_(0, rows, lens - 1)
+            self.kv_len.index_copy_(0, rows, lens)
+            self.q_len.index_fill_(0, rows, 1)
         self.stream.synchronize()
         self.mesh.barrier()
 
