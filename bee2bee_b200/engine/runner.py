@@ -185,9 +185,13 @@ class GpuRunner:
                 used += n
             if batch:
                 chunks.append(batch)
+            # Chunks travel through the pieces as a wavefront: piece i works on chunk c+1 while piece i+1 works on
+            # chunk c.  The handoff slot is flow-controlled on the device (release flag / consumer ack), so no host
+            # barrier is needed between chunks (B2B_PREFILL_BARRIER=1 restores the serialised behaviour).
+            serial = os.environ.get("B2B_PREFILL_BARRIER", "0") == "1"
             for ci, chunk in enumerate(chunks):
                 self._prefill_chunk(chunk)
-                if self.world > 1:
+                if self.world > 1 and serial:
                     self.stream.synchronize()
                     self.mesh.barrier()
             lens = torch.tensor([len(s.prompt) for s in seqs], dtype=i32).to(dev, non_blocking=True)
@@ -319,11 +323,12 @@ class GpuRunner:
             ops.sample(out, tok_tmp, seen=seen_sel, temperature=sel(self.temperature), top_p=sel(self.top_p),
                        rep_penalty=sel(self.rep_pen), seeds=sel(self.seeds), step=self.step_ctr,
                        vocab=self.cfg.vocab_size, softcap=self.cfg.final_softcap)
-            fin = torch.tensor(finals, device=dev)
-            fin_rows = row_idx[fin]
-            if fin_rows.numel():
-                self.seen.index_copy_(0, fin_rows, seen_sel[fin])
-                self._publish_first_tokens(fin_rows, tok_tmp[fin])
+            fin_i = [i for i, f in enumerate(finals) if f]          # host-side selection: no device sync per chunk
+            if fin_i:
+                fin = t(fin_i, torch.int64)
+                fin_rows = t([rows[i] for i in fin_i], torch.int64)
+                self.seen.index_copy_(0, fin_rows, seen_sel.index_select(0, fin))
+                self._publish_first_tokens(fin_rows, tok_tmp.index_select(0, fin))
 
     def _publish_first_tokens(self, rows: torch.Tensor, toks: torch.Tensor) -> None:
         """token ring + history[.., 0] on rank 0 (peer stores when world > 1)."""
