@@ -102,12 +102,13 @@ def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
     if (n_out, k) in SPLITK_OVERRIDE:
         want = SPLITK_OVERRIDE[(n_out, k)]
     else:
-        # measured (tools/layer_sweep.py, Llama-3-8B): the split epilogue costs ~3 us, more with wide
-        # token tiles -> aim for ~1 CTA/SM at bn >= 32, ~2 CTAs/SM at bn = 16; >= 16 k-blocks per CTA
+        # measured (tools/layer_sweep.py, Llama-3-8B, reduce-scatter split-K epilogue): up to ~2 CTAs per SM pay off
+        # (bn=32: qkv 4, o 4, gate/up 1, down 8 -> 100 us/layer; bn=16: 4/4/1/4 -> 92.6 us); >= 16 k-blocks per
+        # CTA, and every CTA of the cluster keeps >= 4 token columns (vector DSMEM stores)
         tiles = (n_out // 128) * ((m_tok + bn - 1) // bn)
-        limit = NUM_SMS if bn >= 32 else 2 * NUM_SMS
+        limit = 256 if bn >= 32 else 200
         want = 1
-        while tiles * want * 2 <= limit and want < 8:
+        while tiles * want * 2 <= limit and want < 8 and bn // (want * 2) >= 4:
             want *= 2
         while want > 1 and (k // 64) // want < 16:
             want //= 2

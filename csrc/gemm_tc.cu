@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int splitk = p.splitk;
   const int krank = (splitk > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = (krank == 0);
+  // split-K reduce-scatter: this CTA finishes token columns [col0, col0 + ncol) of the tile (launcher: splitk | BN)
+  const int ncol = BN / splitk;
+  const int col0 = krank * ncol;
 
   constexpr int BKE = FP8 ? 128 : 64;       // K elements per 128-byte k-block
   const int nkb_total = p.k / BKE;
@@ -221,13 +224,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     }
   } else {
     // ---------------------------------------- epilogue warps: prologue work
+    // Every CTA of a split-K cluster finishes its own slice of token columns [col0, col0 + ncol)
+    // (reduce-scatter, see below), so each CTA only needs the per-token inputs of that slice.
     const int et = threadIdx.x - 64;   // 0..127
     pdl_wait();                        // everything below reads / writes memory of earlier kernels
-    if (leader) {
+    {
       if constexpr (EPI == EPI_QKV_ROPE) {
         // per-token metadata -> smem once: global loads inside the store loop of the epilogue serialise on L2
         // latency (the compiler cannot hoist them above stores that may alias): +8 us at 32 tokens
-        for (int t = et; t < BN; t += 128) {
+        for (int t = col0 + et; t < col0 + ncol; t += 128) {
           const int tok = tok0 + t;
           pos_s[t] = (p.positions != nullptr && tok < p.m_tok) ? p.positions[tok] : 0;
           slot_s[t] = (tok < p.m_tok) ? p.slots[tok] : -1;
@@ -238,20 +243,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
           wait_flag_ge(p.wait_flag, target);
         }
-        // one warp per token, FOUR tokens in flight per warp (the loop is L2-latency bound: a row is
-        // 16 x 128-bit loads per lane, the next row's loads must not wait for this row's reduction)
+        // one warp per token, FOUR tokens x FOUR row segments in flight per lane (the loop is L2-latency
+        // bound: 16 independent 128-bit loads are issued before the first use)
         const int kv8 = p.k / 8;
-        for (int t = warp - 2; t < BN; t += 16) {
+        for (int tr = warp - 2; tr < ncol; tr += 16) {
           float ss[4] = {0.f, 0.f, 0.f, 0.f};
           const uint4* rowp[4];
           bool live[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int tok = tok0 + t + 4 * u;
-            live[u] = (t + 4 * u < BN) && tok < p.m_tok;
+            const int tok = tok0 + col0 + tr + 4 * u;
+            live[u] = (tr + 4 * u < ncol) && tok < p.m_tok;
             rowp[u] = reinterpret_cast<const uint4*>(p.norm_src + static_cast<size_t>(live[u] ? tok : tok0) * p.k);
           }
-          // 4 tokens x 4 row segments = 16 independent 128-bit loads per lane before the first use
           for (int i0 = lane; i0 < kv8; i0 += 128) {
             uint4 v[4][4];
 #pragma unroll
@@ -275,12 +279,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
-            if (lane == 0 && t + 4 * u < BN)
-              rstd_s[t + 4 * u] = live[u] ? rsqrtf(ss[u] / static_cast<float>(p.k) + p.eps) : 0.f;
+            if (lane == 0 && tr + 4 * u < ncol)
+              rstd_s[col0 + tr + 4 * u] = live[u] ? rsqrtf(ss[u] / static_cast<float>(p.k) + p.eps) : 0.f;
           }
         }
       } else {
-        for (int t = et; t < BN; t += 128) {
+        for (int t = col0 + et; t < col0 + ncol; t += 128) {
           const int tok = tok0 + t;
           rstd_s[t] = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
         }
@@ -292,29 +296,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     if (threadIdx.x == 64) B2B_DBG(5);
   }
 
-  // ------------------------------------------------ split-K reduce through DSMEM
-  // After barrier #1 every CTA's main loop has retired, so the leader's stage ring
-  // is free and is reused as the landing zone for the peers' partial accumulators.
-  constexpr int RED_LD = BN + 4;
-  float* red = reinterpret_cast<float*>(smem);   // [splitk-1][128 rows][BN + 4]
+  // ------------------------------------- split-K reduce-scatter through DSMEM
+  // After barrier #1 every CTA's main loop has retired, so all stage rings are free.  CTA r of the cluster owns
+  // the token columns [r*CW, (r+1)*CW): every CTA scatters its partial accumulator column slices into the owners'
+  // landing zones (its own slice included), barrier #2, then every CTA adds the `splitk` partials of its slice and
+  // runs the fused epilogue for those CW tokens only.  Compared with "everything to the leader" the epilogue work
+  // (residual / RoPE / stores) is spread over the cluster and no CTA idles.
   const int q = warp & 3;
   const int row = q * 32 + lane;                 // TMEM lane == weight row within the tile
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  float* red = reinterpret_cast<float*>(smem);   // landing zone [splitk][128 rows][CW + 4]
+  const int CWP = ncol + 4;                      // row pitch in floats (16-byte aligned rows, bank spread)
   if (splitk > 1) {
     cluster_arrive_release();
     cluster_wait_acquire();
-    if (warp >= 2 && !leader) {
-      // partial accumulators -> leader's smem, layout [rank][row][BN + 4] (row-padded so that both
-      // the 128-bit DSMEM stores here and the leader's 128-bit reads are bank-conflict free)
-      const uint32_t remote = mapa_smem(smem_u32(red), 0) +
-                              static_cast<uint32_t>((((krank - 1) * BM + row) * RED_LD) * 4);
+    if (warp >= 2) {
+      const uint32_t zone = smem_u32(red) + static_cast<uint32_t>(((krank * BM + row) * CWP) * 4);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(taddr + c, v);
+        if (ncol >= 4) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          st_dsmem_v4(remote + static_cast<uint32_t>((c + i) * 4), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 16; i += 4) {
+            const int col = c + i, d = col / ncol, off = col - d * ncol;
+            st_dsmem_v4(mapa_smem(zone, static_cast<uint32_t>(d)) + static_cast<uint32_t>(off * 4),
+                        make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = c + i, d = col / ncol, off = col - d * ncol;
+            st_dsmem_f32(mapa_smem(zone, static_cast<uint32_t>(d)) + static_cast<uint32_t>(off * 4), v[i]);
+          }
+        }
       }
     }
     cluster_arrive_release();
@@ -322,9 +337,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   }
 
   // ------------------------------------------------------------ fused epilogue
-  if (warp >= 2 && leader) {
+  if (warp >= 2) {
     const int n_glob = tile_n * BM + row;
-    float* xch = red + (splitk - 1) * BM * RED_LD;   // GLU exchange buffer [BN][64]
+    float* xch = red + splitk * BM * CWP;          // GLU exchange buffer [ncol][64] (behind the landing zone)
     const float bias_v = (p.bias != nullptr) ? p.bias[n_glob] : 0.f;
     // fp8: per-output-row weight scale (the per-token activation scale rides in rstd_s)
     const float wsc = (FP8 && p.w_scale != nullptr) ? p.w_scale[n_glob] : 1.f;
@@ -350,58 +365,72 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
     }
 
+    // accumulators of up to 16 columns starting at local column c (slice-relative)
+    auto load_acc = [&](int c, int n, float* v) {
+      if (splitk == 1) {
+        tmem_ld16(taddr + c, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int r = 0; r < splitk; ++r) {
+          const float* pr = red + (r * BM + row) * CWP + c;
+          if (n >= 4) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (i < n) {
+                const float4 q4 = *reinterpret_cast<const float4*>(pr + i);
+                v[i] += q4.x; v[i + 1] += q4.y; v[i + 2] += q4.z; v[i + 3] += q4.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < n) v[i] += pr[i];
+          }
+        }
+      }
+    };
+
     if constexpr (EPI == EPI_GLU) {
       // phase A: the "up" half (rows 64..127) parks its values in shared memory
       if (row >= 64) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
+        for (int c = 0; c < ncol; c += 16) {
+          const int n = min(16, ncol - c);
           float v[16];
-          tmem_ld16(taddr + c, v);
-          for (int r = 0; r < splitk - 1; ++r) {
-            const float4* pr = reinterpret_cast<const float4*>(red + (r * BM + row) * RED_LD + c);
+          load_acc(c, n, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 q4 = pr[i];
-              v[4 * i] += q4.x; v[4 * i + 1] += q4.y; v[4 * i + 2] += q4.z; v[4 * i + 3] += q4.w;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) xch[(c + i) * 64 + (row - 64)] = v[i];
+          for (int i = 0; i < 16; ++i)
+            if (i < n) xch[(c + i) * 64 + (row - 64)] = v[i];
         }
       }
       epi_bar_sync();
     }
 
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
+    for (int c = 0; c < ncol; c += 16) {
       if (EPI == EPI_GLU && row >= 64) break;
-      if (tok0 + c >= p.m_tok) break;
+      if (tok0 + col0 + c >= p.m_tok) break;
+      const int n = min(16, ncol - c);
       // residual values of the whole chunk first: 16 independent loads in flight (one L2 round trip) instead of
       // one per token between dependent stores
       __nv_bfloat16 resid[16];
       if constexpr (EPI == EPI_RESIDUAL) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int tok = tok0 + c + i;
-          resid[i] = (tok < p.m_tok) ? p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob] : __float2bfloat16_rn(0.f);
+          const int tok = tok0 + col0 + c + i;
+          resid[i] = (i < n && tok < p.m_tok) ? p.residual[static_cast<size_t>(tok) * p.ld_res + n_glob] : __float2bfloat16_rn(0.f);
         }
       }
       float v[16];
-      tmem_ld16(taddr + c, v);
-      for (int r = 0; r < splitk - 1; ++r) {
-        const float4* pr = reinterpret_cast<const float4*>(red + (r * BM + row) * RED_LD + c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 q4 = pr[i];
-          v[4 * i] += q4.x; v[4 * i + 1] += q4.y; v[4 * i + 2] += q4.z; v[4 * i + 3] += q4.w;
-        }
-      }
+      load_acc(c, n, v);
 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int tok = tok0 + c + i;
-        if (tok >= p.m_tok) continue;            // warp-uniform: padded token columns do no work
-        const float rs = rstd_s[c + i];
+        const int lc = col0 + c + i;             // column within the CTA's token tile
+        const int tok = tok0 + lc;
+        if (i >= n || tok >= p.m_tok) continue;  // warp-uniform: padded token columns do no work
+        const float rs = rstd_s[lc];
         const float a = v[i] * rs * wsc + bias_v;
         if constexpr (EPI == EPI_PLAIN) {
           if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = a;
@@ -423,13 +452,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             // lanes (2j, 2j+1) hold (x_j, x_{j+hd/2}) thanks to the offline row interleave
             const float partner = __shfl_xor_sync(0xffffffffu, a, 1);
             float sn, cs;
-            sincosf(static_cast<float>(pos_s[c + i]) * inv_freq, &sn, &cs);
+            sincosf(static_cast<float>(pos_s[lc]) * inv_freq, &sn, &cs);
             o = (lane & 1) ? (a * cs + partner * sn) : (a * cs - partner * sn);
           }
           if (sect == 0) {
             p.q_out[static_cast<size_t>(tok) * q_dim + f_in_sect] = __float2bfloat16_rn(o * p.q_scale);
           } else {
-            const int slot = slot_s[c + i];
+            const int slot = slot_s[lc];
             __nv_bfloat16* dst = (sect == 1 ? p.k_cache : p.v_cache);
             if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
           }
@@ -443,7 +472,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       __threadfence_system();            // my (possibly peer-directed) stores are performed
       epi_bar_sync();
       if (threadIdx.x == 64) {
-        const uint32_t total = gridDim.x * gridDim.y;
+        const uint32_t total = gridDim.x * gridDim.y * gridDim.z;   // every CTA of a split-K cluster stores a slice
         const uint32_t prev = atomicAdd(p.done_counter, 1u);
         if (prev == total - 1) {
           __threadfence_system();
@@ -590,7 +619,7 @@ int gemm_tc_init() {
 }
 
 int gemm_tc_max_splitk(int bn, int epi) {
-  // partial tiles land in the leader's stage ring: (S-1)*(BN+4)*512 B (+ GLU exchange BN*256 B)
+  // reduce-scatter landing zone in every CTA's stage ring: S * 128 rows * (BN/S + 4) floats (+ GLU exchange BN/S * 256 B)
   int stages, stage_bytes;
   switch (bn) {
     case 16: stages = GemmCfg<16>::kStages; stage_bytes = GemmCfg<16>::kStageBytes; break;
@@ -599,9 +628,12 @@ int gemm_tc_max_splitk(int bn, int epi) {
     case 128: stages = GemmCfg<128>::kStages; stage_bytes = GemmCfg<128>::kStageBytes; break;
     default: stages = GemmCfg<256>::kStages; stage_bytes = GemmCfg<256>::kStageBytes; break;
   }
-  int budget = stages * stage_bytes - (epi == EPI_GLU ? bn * 256 : 0);
-  int s = 1 + budget / ((bn + 4) * 512);
-  return s > 8 ? 8 : (s < 1 ? 1 : s);
+  int best = 1;
+  for (int s = 2; s <= 8 && bn / s >= 2; s *= 2) {
+    const int need = s * 128 * (bn / s + 4) * 4 + (epi == EPI_GLU ? (bn / s) * 256 : 0);
+    if (need <= stages * stage_bytes) best = s;
+  }
+  return best;
 }
 
 int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn, cudaStream_t stream) {
@@ -614,6 +646,7 @@ int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn,
   const int smax = gemm_tc_max_splitk(bn, p.epi);
   if (p.splitk > smax) p.splitk = smax;
   if (p.splitk > p.k / bke) p.splitk = p.k / bke;
+  while (p.splitk & (p.splitk - 1)) --p.splitk;      // cluster reduce-scatter: power of two (divides the token tile)
   CUtensorMap tw, tx;
   int r = make_tmap(&tw, w, p.n_out, p.k, p.k, BM, elt);
   if (r) return r;

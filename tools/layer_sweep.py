@@ -27,7 +27,10 @@ for B in [int(os.environ.get("B", "32"))]:
     combos = [dict(qkv=4, o=4, gu=1, down=8), dict(qkv=2, o=4, gu=1, down=4), dict(qkv=4, o=8, gu=2, down=8),
               dict(qkv=2, o=2, gu=1, down=4), dict(qkv=4, o=4, gu=2, down=4), dict(qkv=1, o=1, gu=1, down=1),
               dict(qkv=8, o=8, gu=1, down=8), dict(qkv=2, o=4, gu=2, down=8)]
-    for pdl in (True, False):
+    if os.environ.get('QUICK'):
+        combos = [dict(qkv=2, o=4, gu=1, down=4), dict(qkv=4, o=4, gu=1, down=4), dict(qkv=4, o=4, gu=1, down=8), dict(qkv=4, o=8, gu=1, down=8),
+                  dict(qkv=2, o=4, gu=2, down=4), dict(qkv=4, o=4, gu=2, down=8), dict(qkv=2, o=2, gu=1, down=4), dict(qkv=2, o=4, gu=1, down=8)]
+    for pdl in ((True,) if os.environ.get('QUICK') else (True, False)):
         C.set_pdl(pdl)
         for cb in combos:
             ops.SPLITK_OVERRIDE.clear()
