@@ -13,7 +13,9 @@ Backends: ``GpuRunner`` (hand-written sm_100a kernels; one per GPU, pieces over 
 from __future__ import annotations
 
 import itertools
+import collections
 import queue
+import statistics
 import threading
 import time
 from dataclasses import dataclass, field
@@ -190,6 +192,8 @@ class Engine:
         self._wake = threading.Event()
         self._stop = False
         self._thread: Optional[threading.Thread] = None
+        self.host_ms = {"prefill": 0.0, "decode": 0.0, "collect": 0.0}     # host wall time per scheduler phase
+        self._ttfts: "collections.deque[float]" = collections.deque(maxlen=4096)   # submit -> first token, ms
         self.stats = {"requests": 0, "tokens": 0, "prefill_tokens": 0, "steps": 0, "busy_s": 0.0,
                       "started": time.time()}
 
@@ -245,6 +249,9 @@ class Engine:
                 "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
                 "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
                 "d2h_bytes": self.d2h_bytes, "native_launches": getattr(self.runner, "kernel_launches", 0),
+                "host_ms": dict(self.host_ms),
+                "ttft_ms": ({"count": len(self._ttfts), "p50": statistics.median(self._ttfts),
+                             "p90": sorted(self._ttfts)[int(0.9 * (len(self._ttfts) - 1))]} if self._ttfts else {}),
                 "trace": __import__("bee2bee_b200.utils.tracing", fromlist=["TRACER"]).TRACER.summary()}
 
     # --------------------------------------------------------------- scheduler
@@ -335,9 +342,11 @@ class Engine:
                             seed=r.params.seed if r.params.seed is not None else (r.rid * 2654435761) & 0x7FFFFFFF)
                     for r in admitted]
             from ..utils.tracing import TRACER
+            th = time.perf_counter()
             with TRACER.range(f"prefill[{len(seqs)} seqs]", getattr(self.runner, "stream", None),
                               device_timed=self.gpu):
                 self.runner.prefill(seqs)
+            self.host_ms["prefill"] += (time.perf_counter() - th) * 1e3
             for r in admitted:
                 self._running[r.slot] = r
                 self.stats["prefill_tokens"] += len(r.prompt_ids)
@@ -349,10 +358,14 @@ class Engine:
             return bool(admitted)
         remaining = min(r.params.max_new_tokens - len(r.out_ids) for r in self._running.values())
         n = max(1, min(self.decode_burst, remaining))
+        th = time.perf_counter()
         self.runner.decode(n)
         self.runner.sync()
+        tc = time.perf_counter()
+        self.host_ms["decode"] += (tc - th) * 1e3
         self.stats["steps"] += n
         self._collect(steps=n)
+        self.host_ms["collect"] += (time.perf_counter() - tc) * 1e3
         self.stats["busy_s"] += time.time() - t0
         return True
 
@@ -393,6 +406,8 @@ class Engine:
                     break
                 if not r.t_first:
                     r.t_first = time.time()
+                    if r.t_submit:
+                        self._ttfts.append((r.t_first - r.t_submit) * 1e3)
                 r.out_ids.append(int(tok))
                 self.stats["tokens"] += 1
                 if r.on_token is not None:

@@ -80,7 +80,12 @@ def test_register_status_generate_metrics(gateway):
     r = c.post("/api/p2p/register", json={"link": link}).json()
     assert r["status"] == "registered" and r["model"] == "echo-model" and r["connected"] is True
     assert r["activeNode"] == prov.node.addr
-    st = c.get("/api/p2p/status").json()
+    import time
+    for _ in range(100):                    # the provider's hello (region, services) arrives asynchronously
+        st = c.get("/api/p2p/status").json()
+        if "Test-Region" in st["mesh"] and st["mesh"]["Test-Region"][0]["models"]:
+            break
+        time.sleep(0.05)
     assert st["status"] == "active" and st["poolSize"] >= 1
     node_rows = st["mesh"]["Test-Region"]
     assert node_rows[0]["peer_id"] == prov.node.peer_id and node_rows[0]["models"] == ["echo-model"]

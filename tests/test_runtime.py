@@ -173,6 +173,7 @@ def test_silent_peer_is_dropped_by_pong_timeout():
             await a.connect_bootstrap(b.addr)
             await settle(lambda: b.peer_id in a.peers and a.peers[b.peer_id].get("last_pong_at"))
             b._handlers[P.PING] = lambda conn, data: asyncio.sleep(0)       # b stops answering pings
+            a._bootstrap_addrs.clear()      # no automatic re-dial: the drop must stay observable
             await settle(lambda: b.peer_id not in a.peers, timeout=6)
         finally:
             await a.stop(); await b.stop()
