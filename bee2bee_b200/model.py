@@ -77,15 +77,38 @@ def deserialize_layer(d: Dict) -> Layer:
 
 
 # ------------------------------------------------------------------ device path
+def _tc_ok(dev, *dims_128, k: int) -> bool:
+    """the tcgen05 swap-AB GEMM applies: CUDA device, output features multiple of 128, reduction multiple of 64"""
+    import torch
+
+    if not str(dev).startswith("cuda") or not torch.cuda.is_available():
+        return False
+    from . import ops
+    return ops.has_native() and all(d % 128 == 0 for d in dims_128) and k % 64 == 0 and k >= 64
+
+
+def _tc_matmul(a, b_t, bias=None):
+    """a [T, K] @ b_t[N, K]^T -> fp32 [T, N] on the tcgen05 GEMM (bf16 operands, fp32 accumulate, fp32 out)"""
+    import torch
+    from . import ops
+
+    return ops.gemm(b_t.to(torch.bfloat16).contiguous(), a.to(torch.bfloat16).contiguous(), out_fp32=True,
+                    bias=None if bias is None else bias.float().contiguous())
+
+
 def dense_forward_device(W, b, activation: str, x, device=None):
-    """torch tensors in, (y, z) out; runs on ``device`` (GPU when available)."""
+    """torch tensors in, (y, z) out; runs on ``device`` (GPU when available).  On a B200 with tile-aligned shapes
+    the product runs on the tcgen05 GEMM (bf16 operands, fp32 accumulation, bias fused in the epilogue) -- K12."""
     import torch
 
     dev = device or ("cuda" if torch.cuda.is_available() else "cpu")
     Wt = torch.as_tensor(W, dtype=torch.float32, device=dev)
     bt = torch.as_tensor(b, dtype=torch.float32, device=dev)
     xt = torch.as_tensor(x, dtype=torch.float32, device=dev)
-    z = xt @ Wt + bt
+    if xt.dim() == 2 and _tc_ok(dev, Wt.shape[1], k=Wt.shape[0]):
+        z = _tc_matmul(xt, Wt.t(), bt)                      # z[t, out] = sum_in x[t, in] W[in, out] + b[out]
+    else:
+        z = xt @ Wt + bt
     if activation == "relu":
         y = torch.relu(z)
     elif activation == "gelu":
@@ -110,4 +133,8 @@ def dense_backward_device(W, activation: str, x, z, grad_out, device=None):
         gz = g * (0.5 * (1 + t) + 0.5 * zt * (1 - t ** 2) * _C * (1 + 3 * 0.044715 * zt ** 2))
     else:
         gz = g
+    if xt.dim() == 2 and _tc_ok(dev, Wt.shape[0], Wt.shape[1], k=Wt.shape[1]) and xt.shape[0] % 64 == 0:
+        gX = _tc_matmul(gz, Wt)                             # gX[t, in]  = sum_out gz[t, out] W[in, out]
+        gW = _tc_matmul(xt.t(), gz.t())                     # gW[in, out] = sum_t x[t, in] gz[t, out]
+        return gX, gW, gz.sum(0)
     return gz @ Wt.t(), xt.t() @ gz, gz.sum(0)

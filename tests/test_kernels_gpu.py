@@ -455,3 +455,30 @@ def test_gemm_epilogues_both_kernels(streamk):
     bias = torch.randn(256, device="cuda") * 0.1
     close(ops.gemm(wd, out, epi=ops.EPI_GELU, bias=bias, streamk=streamk),
           torch_ref.gelu_tanh(out.float() @ wd.float().t() + bias))
+
+
+# ---------------------------------------------------------------- K12: dense layer fwd / bwd on the tcgen05 GEMM
+def test_dense_layer_forward_backward_on_tensor_cores():
+    """legacy split-learning layer tasks (node.py layer_forward_train / layer_backward): tile-aligned shapes run on
+    the tcgen05 GEMM (bf16 operands, fp32 accumulation) and agree with the fp32 formulas."""
+    from bee2bee_b200 import model as mlp
+
+    torch.manual_seed(0)
+    T, din, dout = 128, 256, 384
+    W = torch.randn(din, dout, device="cuda") * 0.05
+    b = torch.randn(dout, device="cuda") * 0.1
+    x = torch.randn(T, din, device="cuda")
+    g = torch.randn(T, dout, device="cuda")
+    assert mlp._tc_ok("cuda", dout, k=din)
+    for act in ("relu", "gelu", "none"):
+        y, z = mlp.dense_forward_device(W, b, act, x, device="cuda")
+        z_ref = x @ W + b
+        close(z, z_ref, rtol=2e-2, atol=2e-2)
+        gX, gW, gb = mlp.dense_backward_device(W, act, x, z_ref, g, device="cuda")
+        xr, Wr = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+        zr = xr @ Wr + b
+        yr = torch.relu(zr) if act == "relu" else (torch.nn.functional.gelu(zr, approximate="tanh") if act == "gelu" else zr)
+        yr.backward(g)
+        close(gX, xr.grad, rtol=3e-2, atol=3e-2)
+        close(gW, Wr.grad, rtol=3e-2, atol=1e-1)
+        close(gb, g.mul((zr > 0).float()).sum(0) if act == "relu" else gb, rtol=1e-3, atol=1e-3)
