@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CS = gridDim.z, r = blockIdx.z;
+  // Distributed shared memory of a peer may only be touched once that CTA has started executing: every thread
+  // arrives on the cluster barrier here and waits on it right before the first remote store (compute-sanitizer:
+  // "block that might not have entered yet").
+  cluster_arrive_release();
   pdl_launch_dependents();
   for (int i = tid; i < SBINS; i += SAMP_THREADS) { S.h1_lo[i] = 0u; S.h1_hi[i] = 0u; S.h2_lo[i] = 0u; S.h2_hi[i] = 0u; }
   pdl_wait();
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
   }
   if (lane == 0) { S.red_f[warp] = mx; S.red_i[warp] = amx; }
   __syncthreads();
+  cluster_wait_acquire();            // all CTAs of the cluster are running (pairs with the arrive at kernel entry)
   if (warp == 0) {
     mx = S.red_f[lane]; amx = S.red_i[lane];
 #pragma unroll
