@@ -183,3 +183,67 @@ def test_seeded_sampling_is_reproducible():
     c = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64).generate(
         [[1, 2, 3]], SamplingParams(max_new_tokens=8, temperature=0.9, seed=12, ignore_eos=True))
     assert a == b and a != c
+
+
+# ------------------------------------------------------------------ piece planning / quantisation helpers (CPU)
+def test_piece_units_cover_the_model_and_balance_the_wavefront():
+    from bee2bee_b200.models.config import balanced_split, piece_units, supports_half_layer_pieces
+
+    cfg = resolve_config("llama-3-8b")
+    assert supports_half_layer_pieces(cfg)
+    for n in (1, 2, 4, 8):
+        units = piece_units(cfg, n)
+        assert len(units) == n and units[0][0] == 0 and units[-1][1] == 2 * cfg.n_layers
+        assert all(a[1] == b[0] for a, b in zip(units, units[1:])) and all(u1 > u0 for u0, u1 in units)
+    # the last piece also streams the 1 GB lm_head: it gets the fewest units, nobody gets more than the mean + one layer
+    u8 = piece_units(cfg, 8)
+    sizes = [b - a for a, b in u8]
+    assert sizes[-1] == min(sizes) and max(sizes) <= 9 and any(a % 2 or b % 2 for a, b in u8)   # half-layer cuts are used
+    # whole-layer fallback for graphs whose boundary GEMMs are not the fused kinds (post-norms / LayerNorm)
+    for name in ("gemma-2-2b", "distilgpt2"):
+        c = resolve_config(name)
+        assert not supports_half_layer_pieces(c)
+        assert piece_units(c, 2) == [(2 * r.start, 2 * r.stop) for r in balanced_split(c, 2)]
+    # explicit bounds (tests / experiments)
+    tiny = resolve_config("tiny-llama")
+    assert piece_units(tiny, 2, [0, 3, 8]) == [(0, 3), (3, 8)]
+    with pytest.raises(AssertionError):
+        piece_units(tiny, 2, [0, 9])
+
+
+def test_mx_block_scaled_quantisation_roundtrip_cpu():
+    """OCP-MX e4m3: one power-of-two scale per 32 K elements; chunk layout used by tcgen05.cp is a pure permutation."""
+    from bee2bee_b200 import ops
+
+    torch.manual_seed(0)
+    w = (torch.randn(256, 512) * 0.05 * torch.exp2(torch.randint(-5, 5, (256, 16)).float()).repeat_interleave(32, 1)).bfloat16()
+    q, chunks = ops.quantize_weight_mxfp8(w)
+    assert q.dtype == torch.float8_e4m3fn and chunks.dtype == torch.uint8 and chunks.numel() == (256 // 128) * (512 // 128) * 512
+    sf = ops.mx_unchunk(chunks, 256, 512, 128)
+    assert torch.equal(ops.mx_chunk_layout(sf), chunks)
+    # byte (r % 32) * 16 + (r / 32) * 4 + k-block inside the 512-byte chunk of (row tile, 128-K chunk)
+    r, kb = 200, 13
+    off = ((r // 128) * 4 + kb // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + kb % 4
+    assert chunks[off] == sf[r, kb]
+    deq = ops.mx_dequant(q, sf)
+    blocks = w.float().view(256, 16, 32)
+    amax = blocks.abs().amax(-1, keepdim=True)
+    err = (deq.view(256, 16, 32) - blocks).abs()
+    assert (err <= 0.0625 * blocks.abs() + 1e-3 * amax).all()
+    # scales are the smallest powers of two that keep |q| <= 448
+    scale = torch.exp2(sf.float() - 127)
+    assert (amax.squeeze(-1) / scale <= 448.0 + 1e-3).all() and (amax.squeeze(-1) / (scale / 2) > 448.0 - 1e-3)[amax.squeeze(-1) > 0].all()
+
+
+def test_split_k_heuristic_matches_the_measured_optimum():
+    from unittest import mock
+
+    from bee2bee_b200 import ops
+
+    fake = mock.Mock(gemm_max_splitk=lambda bn, epi: 8)
+    shapes = dict(qkv=(6144, 4096), o=(4096, 4096), gu=(28672, 4096), down=(4096, 14336), head=(128256, 4096))
+    with mock.patch.object(ops, "native", lambda: fake):
+        pick = lambda bn, m: {k: ops.pick_splitk(n, m, kk, bn, 0) for k, (n, kk) in shapes.items()}
+        assert pick(32, 32) == dict(qkv=4, o=4, gu=1, down=8, head=1)      # profiles/raw/layer_sweep_reduce_scatter.txt
+        assert pick(16, 1) == dict(qkv=4, o=4, gu=1, down=4, head=1)       # >= 4 token columns per CTA of the cluster
+        assert all(v == 1 for v in pick(256, 4096).values())               # prefill: tiles already fill the machine
