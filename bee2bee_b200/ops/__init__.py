@@ -92,6 +92,10 @@ def pick_bn(m_tok: int) -> int:
 #: use the persistent stream-K kernel for token tiles <= 64 (decode); False = cluster split-K kernel
 STREAMK = os.environ.get("B2B_STREAMK", "0") != "0"
 
+#: EXPERIMENTAL (untested on hardware in round 1, default off): cluster size of the TMA-multicast prefill GEMM (2 or 4);
+#: applies to bf16 GEMMs with token tiles of 128 / 256 and no split-K, everything else ignores it
+GEMM_MC = int(os.environ.get("B2B_GEMM_MC", "0"))
+
 #: (n_out, k) -> split-K override (tuning / sweeps)
 SPLITK_OVERRIDE = {}
 
@@ -129,7 +133,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
          dbg: int = 0, w_scale: Optional[torch.Tensor] = None, streamk: Optional[bool] = None,
-         sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+         sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -151,7 +155,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk, sfa, sfb)
+                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk, sfa, sfb, GEMM_MC if mc < 0 else mc)
     return out
 
 

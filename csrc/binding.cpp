@@ -46,7 +46,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
           int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale, bool streamk,
-          const OptT& sfa, const OptT& sfb) {
+          const OptT& sfa, const OptT& sfb, int64_t mc) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
@@ -78,6 +78,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;
   p.fp8 = fp8 ? 1 : 0;
+  p.mc = static_cast<int>(mc);      // experimental TMA-multicast cluster (0/1 = off)
   p.w_scale = ptr_or_null<const float>(w_scale);
   p.sfa = fp8 ? ptr_or_null<const uint8_t>(sfa) : nullptr;
   p.sfb = fp8 ? ptr_or_null<const uint8_t>(sfb) : nullptr;

@@ -24,6 +24,7 @@ struct GemmParams {
   int out_fp32;       // EPI_PLAIN only: write fp32 (logits)
   int act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
   int fp8;            // operands are e4m3 (W8A8): W [N,K] and X [T,K] one byte per element
+  int mc;             // EXPERIMENTAL (0/1 = off): cluster of `mc` CTAs along the weight-tile axis shares the token tile by TMA multicast
   const float* w_scale;  // fp8: per-output-row dequant scale [n_out] (activation scale rides in `rstd`)
   // MX fp8 (tcgen05 kind::mxf8f6f4.block_scale): UE8M0 scale per 32 K elements, pre-arranged in 512-byte
   // chunks per (128 rows, 128 K): byte (r % 32) * 16 + (r / 32) * 4 + (k / 32) % 4.  sfa: weights

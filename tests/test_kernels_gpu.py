@@ -1,6 +1,8 @@
 """Numerics of every hand-written sm_100a kernel against a plain PyTorch fp32 reference."""
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -482,3 +484,16 @@ def test_dense_layer_forward_backward_on_tensor_cores():
         close(gX, xr.grad, rtol=3e-2, atol=3e-2)
         close(gW, Wr.grad, rtol=3e-2, atol=1e-1)
         close(gb, g.mul((zr > 0).float()).sum(0) if act == "relu" else gb, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------- experimental: TMA-multicast cluster GEMM (opt-in, round-2 bring-up)
+@pytest.mark.skipif(os.environ.get("B2B_TEST_EXPERIMENTAL") != "1", reason="experimental kernel path: set B2B_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mc", [2, 4])
+@pytest.mark.parametrize("m", [512, 300])
+def test_gemm_multicast_cluster(mc, m):
+    n, k = 1024, 1024
+    w, x, res = bf(n, k, scale=0.05, seed=1), bf(m, k, seed=2), bf(m, n, seed=3)
+    ref = x.float() @ w.float().t()
+    for bn in (128, 256):
+        close(ops.gemm(w, x, bn=bn, splitk=1, mc=mc), ref, rtol=2e-2, atol=2e-2)
+        close(ops.gemm(w, x, bn=bn, splitk=1, mc=mc, epi=ops.EPI_RESIDUAL, residual=res), ref + res.float(), rtol=2e-2, atol=2e-2)
