@@ -79,6 +79,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// EXPERIMENTAL (P_TMEM variant, not yet run on hardware): D[tmem] (+)= A[tmem] * B[smem] -- the A operand (P) is read
+// from tensor memory: lane = row, 16-bit elements packed two per 32-bit column (element 2j in the low half).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32_bits(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+      "%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // MN-major 128B-swizzled operand (rows = K index, 128-byte rows of 64 contiguous N elements):
 // LBO = distance between 64-element N blocks, SBO = distance between 8-row K groups (1024 B).
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -140,7 +164,9 @@ struct AtcCfg {
   static constexpr int kMinCtas = (D <= 128) ? 2 : 1;                  // two CTAs per SM: one's softmax hides the other's MMAs
 };
 
-template <int D, bool SOFTCAP>
+// P_TMEM (EXPERIMENTAL, default false): P stays in tensor memory (written over the first BKV/2 columns of the S buffer
+// it was computed from) and feeds the PV MMA as a TMEM A operand; no P tile in shared memory, no fence.proxy.async.
+template <int D, bool SOFTCAP, bool P_TMEM = false>
 __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::kMinCtas)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p, const int G, const int QB) {
@@ -257,9 +283,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t a = make_sw128_kmajor_desc(smem_u32(p_s)) + static_cast<uint64_t>(kk * 2);
           const uint64_t b = make_sw128_mnmajor_desc(smem_u32(v_s + s * Cfg::kKVBytes + kk * (16 * 128)), BKV * 128);
-          umma_bf16(tmem + O_COL, a, b, idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
+          if constexpr (P_TMEM) {
+            // 16 keys of P = 8 packed columns of the S buffer this tile came from
+            umma_bf16_ts(tmem + O_COL, tmem + S_COL + static_cast<uint32_t>(s) * BKV + kk * 8, b, idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
+          } else {
+            const uint64_t a = make_sw128_kmajor_desc(smem_u32(p_s)) + static_cast<uint64_t>(kk * 2);
+            umma_bf16(tmem + O_COL, a, b, idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&v_empty[s]);
         umma_commit(pv_done);
@@ -326,6 +357,19 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       // P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile (A operand of the PV MMA)
       const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;          // fully masked so far: exp2(-inf - 0) = 0
       float lsum = 0.f;
+      if constexpr (P_TMEM) {
+        uint32_t pk[BKV / 2];            // bf16 pairs: key 2j in the low half of column j
+#pragma unroll
+        for (int j = 0; j < BKV / 2; ++j) {
+          const float p0 = exp2f(__uint_as_float(r[2 * j]) - mr);
+          const float p1 = exp2f(__uint_as_float(r[2 * j + 1]) - mr);
+          lsum += p0 + p1;
+          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        static_assert(BKV == 64, "P_TMEM packs one 64-key tile into 32 columns");
+        tmem_st32_bits(s_addr, pk);      // over the (already consumed) scores of this tile
+      } else {
       uint8_t* ptile = p_s + row * 128;
 #pragma unroll
       for (int j = 0; j < BKV / 8; ++j) {
@@ -340,8 +384,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         *reinterpret_cast<uint4*>(ptile + ((j ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      }
       l = l * alpha + lsum;
-      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      if constexpr (!P_TMEM) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
@@ -394,7 +439,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 }
 
-template <int D, bool SOFTCAP>
+template <int D, bool SOFTCAP, bool P_TMEM>
 int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
                   int seqs, int qblocks, cudaStream_t s) {
   using Cfg = AtcCfg<D>;
@@ -402,20 +447,24 @@ int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D, SOFTCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D, SOFTCAP, P_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     set[dev] = true;
   }
-  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, SOFTCAP>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
+  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, SOFTCAP, P_TMEM>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
                                         Cfg::kSmemBytes, s, 1, tq, tk, tv, p, G, QB));
 }
 
 template <int D>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
               int seqs, int qblocks, cudaStream_t s) {
-  return p.softcap > 0.f ? launch_tc_cap<D, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
-                         : launch_tc_cap<D, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+  static const bool p_tmem = [] { const char* e = std::getenv("B2B_ATTN_P_TMEM"); return e && e[0] == '1'; }();   // experimental
+  if (p_tmem)
+    return p.softcap > 0.f ? launch_tc_cap<D, true, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
+                           : launch_tc_cap<D, false, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+  return p.softcap > 0.f ? launch_tc_cap<D, true, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
+                         : launch_tc_cap<D, false, false>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
 }
 
 }  // namespace

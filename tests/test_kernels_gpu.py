@@ -497,3 +497,18 @@ def test_gemm_multicast_cluster(mc, m):
     for bn in (128, 256):
         close(ops.gemm(w, x, bn=bn, splitk=1, mc=mc), ref, rtol=2e-2, atol=2e-2)
         close(ops.gemm(w, x, bn=bn, splitk=1, mc=mc, epi=ops.EPI_RESIDUAL, residual=res), ref + res.float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.skipif(os.environ.get("B2B_TEST_EXPERIMENTAL") != "1", reason="experimental kernel path: set B2B_TEST_EXPERIMENTAL=1")
+def test_attention_p_in_tmem_experimental():
+    """P kept in tensor memory (TS-form tcgen05.mma): the numerics script must report the same error levels."""
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "attn_tc_check.py")], capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, B2B_ATTN_P_TMEM="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    errs = [float(x) for x in re.findall(r"max_err ([0-9.]+)", out.stdout)]
+    assert len(errs) >= 5 and max(errs) < 0.03, out.stdout
