@@ -264,11 +264,15 @@ def piece_units(cfg: "ModelConfig", pieces: int, bounds: Optional[List[int]] = N
     pieces = max(1, min(pieces, cfg.n_layers))
     if pieces == 1 or not supports_half_layer_pieces(cfg):
         return [(2 * r.start, 2 * r.stop) for r in balanced_split(cfg, pieces)]
+    # stage time model fitted to the measured decode step (profiles/decode_layer_breakdown.md, B200, 32 sequences):
+    # weight bytes at the measured 6.4 TB/s plus ~7 us per kernel launch; the last piece adds the lm_head GEMM and the
+    # 30 us sampler.  Llama-3-8B: attention block 34 us (measured 36.6), MLP block 69 (65), head 201 (213).
     h, f = cfg.hidden_size, cfg.ffn_size
-    launch = 64e6 / 2                                    # ~10 us at 6.4 TB/s, in bf16 elements
-    attn = h * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.q_dim * h + 3 * launch
-    mlp = 3 * h * f + 2 * launch
-    head = cfg.vocab_size * h + 2 * launch
+    us_per_elem = 2.0 / 6.4e6                            # bf16 element -> microseconds of HBM streaming
+    launch = 7.0
+    attn = (h * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.q_dim * h) * us_per_elem + 3 * launch
+    mlp = 3 * h * f * us_per_elem + 2 * launch
+    head = cfg.vocab_size * h * us_per_elem + launch + 30.0
     cost = [attn if u % 2 == 0 else mlp for u in range(U)]
     pre = [0.0]
     for c in cost:
