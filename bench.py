@@ -188,7 +188,7 @@ def run_ours(args):
     if not args.no_e2e:
         sp = SamplingParams(max_new_tokens=K, temperature=0.7, top_p=0.95, repetition_penalty=1.15, ignore_eos=True,
                             seed=7)
-        eng.decode_burst = 32
+        eng.decode_burst = min(K, 64)      # tokens are read back once per burst
         eng.generate(prompts[: min(total, 4)], SamplingParams(max_new_tokens=4, ignore_eos=True))   # warm
         eng.h2d_bytes = eng.d2h_bytes = 0
         h0 = runner.h2d_bytes
