@@ -284,7 +284,7 @@ def piece_units(cfg: "ModelConfig", pieces: int, bounds: Optional[List[int]] = N
     best[0][0] = 0.0
     for k in range(1, pieces + 1):
         for u in range(k, U + 1):
-            for v in range(k - 1, u):
+            for v in range(k - 1, u - 1):          # every piece spans >= 2 units (no lone attention / MLP block)
                 if best[k - 1][v] == INF:
                     continue
                 stage = pre[u] - pre[v] + (head if (k == pieces and u == U) else 0.0)
