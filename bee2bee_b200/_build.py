@@ -22,7 +22,7 @@ BUILD = ROOT / "build" / "obj"
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
-CU_SOURCES = ["gemm_tc.cu", "gemm_sk.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "sampler.cu"]
+CU_SOURCES = ["gemm_tc.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "sampler.cu"]
 CPP_SOURCES = ["peer.cpp", "binding.cpp"]
 
 NVCC_FLAGS = [

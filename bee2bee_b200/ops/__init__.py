@@ -89,18 +89,28 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
-#: use the persistent stream-K kernel for token tiles <= 64 (decode); False = cluster split-K kernel
-STREAMK = os.environ.get("B2B_STREAMK", "0") != "0"
-
 #: EXPERIMENTAL (untested on hardware in round 1, default off): cluster size of the TMA-multicast prefill GEMM (2 or 4);
 #: applies to bf16 GEMMs with token tiles of 128 / 256 and no split-K, everything else ignores it
 GEMM_MC = int(os.environ.get("B2B_GEMM_MC", "0"))
+
+#: weight k-blocks (128 rows x 128 B each) a GEMM CTA prefetches into L2 ahead of its shared-memory ring while it
+#: waits for its producer kernel.  MEASURED NEGATIVE on B200 (profiles/l2_prefetch.md: 99.6 -> 102..115 us per layer):
+#: the prefetch flood delays the latency-bound kernel it overlaps with (attention, split-K epilogues) by more than the
+#: L2 hits save, so the default is 0 = off.  +1024: up front only, +2048: LSU prefetch, +4096: no evict_first on W.
+L2_PREFETCH = int(os.environ.get("B2B_L2_PREFETCH", "0"))
+
+#: shared-memory ring depth of the decode GEMMs (0 = per-token-tile default); fewer stages -> more CTAs per SM, so the
+#: next kernel of a PDL chain becomes resident (and prefetches its weights) while the current one still runs
+GEMM_STAGES = int(os.environ.get("B2B_GEMM_STAGES", "0"))
+
+#: tuning hook: {"buf": int64 cuda tensor, "off": 0, "log": []} makes every GEMM record a per-CTA timeline
+TIMELINE = None
 
 #: (n_out, k) -> split-K override (tuning / sweeps)
 SPLITK_OVERRIDE = {}
 
 
-def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
+def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int, stages: int = 0) -> int:
     """Cluster size along K.  Powers of two only: odd cluster sizes (6, 7) schedule poorly on the
     GPC grid (ncu: launch__cluster_max_active 22 for size 6 vs 74 for size 4)."""
     if (n_out, k) in SPLITK_OVERRIDE:
@@ -117,7 +127,7 @@ def pick_splitk(n_out: int, m_tok: int, k: int, bn: int, epi: int) -> int:
         while want > 1 and (k // 64) // want < 16:
             want //= 2
     want = min(want, 8, max(1, (k // 64) // 2))
-    cap = native().gemm_max_splitk(bn, epi)
+    cap = native().gemm_max_splitk(bn, epi, stages)
     while want > cap:
         want //= 2
     return max(1, want)
@@ -132,15 +142,18 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          out_ptr: int = 0, ld_out: int = 0, residual_ptr: int = 0, ld_res: int = 0,
          wait_flag: int = 0, wait_epoch: int = 0, signal_flag: int = 0, signal_epoch: int = 0,
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
-         dbg: int = 0, w_scale: Optional[torch.Tensor] = None, streamk: Optional[bool] = None,
-         sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1) -> Optional[torch.Tensor]:
+         dbg: int = 0, w_scale: Optional[torch.Tensor] = None,
+         sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1, pf: int = -1,
+         stages: int = -1) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
     if bn <= 0:
         bn = pick_bn_mx(m_tok) if sfa is not None else pick_bn(m_tok)
+    if stages < 0:
+        stages = GEMM_STAGES if bn <= 64 else 0
     if splitk <= 0:
-        splitk = pick_splitk(n_out, m_tok, k, bn, epi)
+        splitk = pick_splitk(n_out, m_tok, k, bn, epi, stages)
     if epi == EPI_QKV_ROPE:
         o_ptr, ldo = 0, 0
     elif out_ptr:
@@ -152,10 +165,18 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
         o_ptr, ldo = out.data_ptr(), out.stride(0)
     if residual is not None:
         residual_ptr, ld_res = residual.data_ptr(), residual.stride(0)
+    if TIMELINE is not None and not dbg:
+        # per-CTA %globaltimer stamps (tools/layer_timeline.py): every GEMM call gets its own slice of the buffer
+        n_cta = (n_out // 128) * ((m_tok + bn - 1) // bn) * splitk
+        dbg = TIMELINE["buf"].data_ptr() + TIMELINE["off"] * 8
+        TIMELINE["log"].append((epi, n_out, k, splitk, TIMELINE["off"], n_cta))
+        TIMELINE["off"] += n_cta * 8
+        assert TIMELINE["off"] <= TIMELINE["buf"].numel()
     native().gemm(w, x, o_ptr, ldo, epi, bn, splitk, residual_ptr, ld_res, bias, rstd, norm_from_x, eps, act_gelu,
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
-                  ack_flag, dbg, w_scale, STREAMK if streamk is None else streamk, sfa, sfb, GEMM_MC if mc < 0 else mc)
+                  ack_flag, dbg, w_scale, sfa, sfb, GEMM_MC if mc < 0 else mc,
+                  L2_PREFETCH if pf < 0 else pf, stages)
     return out
 
 

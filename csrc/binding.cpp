@@ -45,8 +45,8 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, double rope_theta, double q_scale,
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
-          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale, bool streamk,
-          const OptT& sfa, const OptT& sfb, int64_t mc) {
+          int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale,
+          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
@@ -78,6 +78,9 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;
   p.fp8 = fp8 ? 1 : 0;
+  p.stages = static_cast<int>(stages);
+  p.pf_tiles = static_cast<int>(pf_tiles % 1024);
+  p.pf_mode = static_cast<int>(pf_tiles / 1024);     // tuning: bits 0-1 prefetch variant, bit 2 = weights loaded without evict_first
   p.mc = static_cast<int>(mc);      // experimental TMA-multicast cluster (0/1 = off)
   p.w_scale = ptr_or_null<const float>(w_scale);
   p.sfa = fp8 ? ptr_or_null<const uint8_t>(sfa) : nullptr;
@@ -119,27 +122,19 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   }
   if (p.epi == b2b::EPI_RESIDUAL) TORCH_CHECK(p.residual != nullptr, "residual epilogue needs residual");
   if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
-  if (streamk && bn <= 64 && p.dbg == nullptr && p.sfa == nullptr) {
-    const int r = b2b::launch_gemm_sk(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream());
-    if (r != -5) {
-      check(r, "gemm_sk");
-      return;
-    }
-  }
   check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
 }
 
 void set_pdl(bool on) { b2b::g_pdl_mode = on ? 1 : 0; }
 bool get_pdl() { return b2b::pdl_enabled(); }
 
-int64_t gemm_max_splitk(int64_t bn, int64_t epi) {
-  return b2b::gemm_tc_max_splitk(static_cast<int>(bn), static_cast<int>(epi));
+int64_t gemm_max_splitk(int64_t bn, int64_t epi, int64_t stages) {
+  return b2b::gemm_tc_max_splitk(static_cast<int>(bn), static_cast<int>(epi), static_cast<int>(stages));
 }
 
 void init_kernels(int64_t device) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   check(b2b::gemm_tc_init(), "gemm_tc_init");
-  check(b2b::gemm_sk_init(), "gemm_sk_init");
   check(b2b::attention_init(), "attention_init");
 }
 

@@ -102,6 +102,13 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUte
       "h"(cta_mask)
       : "memory");
 }
+// L2-only prefetch of a tile (no shared-memory destination, no mbarrier): keeps HBM busy with the weight tiles a CTA
+// will need beyond its shared-memory ring while the kernel still waits on its producer (PDL / peer flag).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

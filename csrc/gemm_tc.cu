@@ -52,7 +52,8 @@ struct GemmCfg {
   static constexpr int kSfBytes = kSfaBytes + kSfbBytes;
   static constexpr int kSfCol = kTmemCols;                      // first scale-factor column (2 x 16 columns)
   static constexpr int kTmemColsMx = BN <= 32 ? 64 : (BN == 64 ? 128 : (BN == 128 ? 256 : 512));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 12 + kStages * kSfBytes;
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 12 + stages * kSfBytes; }
+  static constexpr int kSmemBytes = smem_bytes(kStages);
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   constexpr bool MCAST = MC > 1;
   constexpr uint16_t MC_MASK = static_cast<uint16_t>((1u << MC) - 1u);
   static_assert(!MCAST || (QM == 0 && BN % MC == 0 && (BN / MC) % 8 == 0), "multicast: bf16, token tile divisible into 8-row groups");
-  constexpr int STAGES = Cfg::kStages;
+  const int STAGES = p.stages;            // ring depth (runtime: 2..Cfg::kStages; fewer stages = more CTAs per SM)
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
   constexpr uint32_t TX_BYTES = STAGE_BYTES + (MX ? Cfg::kSfBytes : 0);
   constexpr uint32_t TCOLS = MX ? Cfg::kTmemColsMx : Cfg::kTmemCols;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint64_t pol_w = l2_policy_evict_first();   // weights: streamed once
+      const uint64_t pol_w = (p.pf_mode & 4) ? l2_policy_evict_last() : l2_policy_evict_first();   // weights: streamed once
       const uint64_t pol_x = l2_policy_evict_last();    // activations: re-read by every CTA
       // Weight tiles depend on no earlier kernel: fill the ring with them first, THEN wait for
       // the producer of the activations (previous kernel via PDL, upstream piece via its flag).
@@ -169,6 +170,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_arrive_expect_tx(&full_bar[i], TX_BYTES);
         tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BKE, tile_n * BM, pol_w);
         if constexpr (MX) bulk_load(sf_s + i * Cfg::kSfBytes, sfa_g + static_cast<size_t>(i) * Cfg::kSfaBytes, Cfg::kSfaBytes, &full_bar[i]);
+      }
+      // ... and keep HBM streaming while we wait: L2 prefetch of the next `pf` weight k-blocks behind the ring.  The
+      // kernel boundary (previous epilogue / split-K reduce / flag hop / our own 1/rms pass) otherwise leaves HBM idle
+      // for 5-8 us per GEMM; the ring alone only covers STAGES x 16 KB per CTA.
+      const int pf = ((p.pf_mode & 3) == 2) ? 0 : p.pf_tiles;
+      const bool pf_roll = (p.pf_mode & 3) == 0;
+      {
+        const int pf_first = (nkb < npre + pf) ? nkb : npre + pf;
+        for (int i = npre; i < pf_first; ++i) tma_prefetch_l2_2d(&tmap_w, (kb_begin + i) * BKE, tile_n * BM);
       }
       pdl_wait();
       if (p.wait_flag != nullptr) {
@@ -188,9 +198,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
       int kb = npre;
       B2B_DBG(2);
+      int s = 0;                 // kb % STAGES
+      uint32_t ph = 1;           // (kb / STAGES) & 1 -- first refill round
       for (; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+        if (pf_roll && pf > 0 && kb + pf < nkb) tma_prefetch_l2_2d(&tmap_w, (kb_begin + kb + pf) * BKE, tile_n * BM);
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
         tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BKE,
@@ -205,14 +216,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           bulk_load(sf_s + s * Cfg::kSfBytes, sfa_g + static_cast<size_t>(kb) * Cfg::kSfaBytes, Cfg::kSfaBytes, &full_bar[s]);
           bulk_load(sf_s + s * Cfg::kSfBytes + Cfg::kSfaBytes, sfb_g + static_cast<size_t>(kb) * Cfg::kSfbBytes, Cfg::kSfbBytes, &full_bar[s]);
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc = MX ? make_idesc_mxf8(BM, BN) : (FP8 ? make_idesc_e4m3(BM, BN) : make_idesc_bf16(BM, BN));
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
@@ -245,12 +257,22 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (kb == nkb - 1) { umma_commit(tmem_full_bar); B2B_DBG(4); }   // accumulator complete
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else {
     // ---------------------------------------- epilogue warps: prologue work
     // Every CTA of a split-K cluster finishes its own slice of token columns [col0, col0 + ncol)
     // (reduce-scatter, see below), so each CTA only needs the per-token inputs of that slice.
     const int et = threadIdx.x - 64;   // 0..127
+    if ((p.pf_mode & 3) == 2 && p.pf_tiles > 0) {
+      // LSU variant of the L2 weight prefetch: thread `et` owns weight row `et` of the tile
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      const int last = (nkb < npre + p.pf_tiles) ? nkb : npre + p.pf_tiles;
+      const uint8_t* rowp = reinterpret_cast<const uint8_t*>(p.w_base) +
+                            (static_cast<size_t>(tile_n) * BM + et) * static_cast<size_t>(p.k) * (FP8 ? 1 : 2);
+      for (int j = npre; j < last; ++j)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + static_cast<size_t>(kb_begin + j) * ROW_BYTES));
+    }
     pdl_wait();                        // everything below reads / writes memory of earlier kernels
     {
       if constexpr (EPI == EPI_QKV_ROPE) {
@@ -582,15 +604,17 @@ int make_tmap_shared(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 template <int BN, int EPI, int QM>
 static int launch_bn_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};      // per device: one process may drive several GPUs (enable_peer_access path)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, QM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    if (dev < 64) attr_set[dev] = true;
   }
   return static_cast<int>(launch_kernel(gemm_tc_kernel<BN, EPI, QM>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, p.splitk),
-                                        dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(p.splitk), tw, tx, p));
+                                        dim3(192), Cfg::smem_bytes(p.stages), stream, static_cast<unsigned>(p.splitk), tw, tx, p));
 }
 
 // EXPERIMENTAL multicast launch (bf16, token tiles of 128 / 256, no split-K): cluster of MC CTAs along grid.x
@@ -607,7 +631,7 @@ static int launch_mc(const GemmParams& p, const CUtensorMap& tw, const CUtensorM
     attr_set[dev] = true;
   }
   return static_cast<int>(launch_kernel_cx(gemm_tc_kernel<BN, EPI, 0, MC>, dim3(p.n_out / BM, (p.m_tok + BN - 1) / BN, 1),
-                                           dim3(192), Cfg::kSmemBytes, stream, static_cast<unsigned>(MC), tw, tx_slice, p));
+                                           dim3(192), Cfg::smem_bytes(p.stages), stream, static_cast<unsigned>(MC), tw, tx_slice, p));
 }
 template <int BN, int MC>
 static int launch_mc_epi(const GemmParams& p, const CUtensorMap& tw, const CUtensorMap& tx_slice, cudaStream_t stream) {
@@ -675,15 +699,27 @@ int gemm_tc_init() {
   return get_encode() ? 0 : -1;
 }
 
-int gemm_tc_max_splitk(int bn, int epi) {
-  // reduce-scatter landing zone in every CTA's stage ring: S * 128 rows * (BN/S + 4) floats (+ GLU exchange BN/S * 256 B)
-  int stages, stage_bytes;
+int gemm_tc_default_stages(int bn) {
   switch (bn) {
-    case 16: stages = GemmCfg<16>::kStages; stage_bytes = GemmCfg<16>::kStageBytes; break;
-    case 32: stages = GemmCfg<32>::kStages; stage_bytes = GemmCfg<32>::kStageBytes; break;
-    case 64: stages = GemmCfg<64>::kStages; stage_bytes = GemmCfg<64>::kStageBytes; break;
-    case 128: stages = GemmCfg<128>::kStages; stage_bytes = GemmCfg<128>::kStageBytes; break;
-    default: stages = GemmCfg<256>::kStages; stage_bytes = GemmCfg<256>::kStageBytes; break;
+    case 16: return GemmCfg<16>::kStages;
+    case 32: return GemmCfg<32>::kStages;
+    case 64: return GemmCfg<64>::kStages;
+    case 128: return GemmCfg<128>::kStages;
+    default: return GemmCfg<256>::kStages;
+  }
+}
+
+int gemm_tc_max_splitk(int bn, int epi, int stages) {
+  // reduce-scatter landing zone in every CTA's stage ring: S * 128 rows * (BN/S + 4) floats (+ GLU exchange BN/S * 256 B)
+  int stage_bytes;
+  const int dflt = gemm_tc_default_stages(bn);
+  if (stages <= 0 || stages > dflt) stages = dflt;
+  switch (bn) {
+    case 16: stage_bytes = GemmCfg<16>::kStageBytes; break;
+    case 32: stage_bytes = GemmCfg<32>::kStageBytes; break;
+    case 64: stage_bytes = GemmCfg<64>::kStageBytes; break;
+    case 128: stage_bytes = GemmCfg<128>::kStageBytes; break;
+    default: stage_bytes = GemmCfg<256>::kStageBytes; break;
   }
   int best = 1;
   for (int s = 2; s <= 8 && bn / s >= 2; s *= 2) {
@@ -695,12 +731,18 @@ int gemm_tc_max_splitk(int bn, int epi) {
 
 int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn, cudaStream_t stream) {
   GemmParams p = p_in;
+  p.w_base = w;
   const int elt = p.fp8 ? 1 : 2;
   const int bke = ROW_BYTES / elt;
   if (p.n_out % BM != 0 || p.k % bke != 0 || p.m_tok <= 0) return -2;
   if (p.splitk < 1) p.splitk = 1;
   if (p.splitk > 8) p.splitk = 8;
-  const int smax = gemm_tc_max_splitk(bn, p.epi);
+  {
+    const int dflt = gemm_tc_default_stages(bn);
+    if (p.stages <= 0 || p.stages > dflt) p.stages = dflt;
+    if (p.stages < 2) p.stages = 2;
+  }
+  const int smax = gemm_tc_max_splitk(bn, p.epi, p.stages);
   if (p.splitk > smax) p.splitk = smax;
   if (p.splitk > p.k / bke) p.splitk = p.k / bke;
   while (p.splitk & (p.splitk - 1)) --p.splitk;      // cluster reduce-scatter: power of two (divides the token tile)

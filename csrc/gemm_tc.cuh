@@ -24,7 +24,11 @@ struct GemmParams {
   int out_fp32;       // EPI_PLAIN only: write fp32 (logits)
   int act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
   int fp8;            // operands are e4m3 (W8A8): W [N,K] and X [T,K] one byte per element
+  int stages;         // shared-memory ring depth (0 = the token tile's default)
+  int pf_mode;        // tuning: 0 = TMA prefetch up front + rolling, 1 = TMA up front only, 2 = LSU prefetch.global.L2 by the epilogue warps
+  int pf_tiles;       // weight k-blocks prefetched into L2 ahead of the shared-memory ring (0 = off)
   int mc;             // EXPERIMENTAL (0/1 = off): cluster of `mc` CTAs along the weight-tile axis shares the token tile by TMA multicast
+  const void* w_base;    // weight matrix base (LSU prefetch variant)
   const float* w_scale;  // fp8: per-output-row dequant scale [n_out] (activation scale rides in `rstd`)
   // MX fp8 (tcgen05 kind::mxf8f6f4.block_scale): UE8M0 scale per 32 K elements, pre-arranged in 512-byte
   // chunks per (128 rows, 128 K): byte (r % 32) * 16 + (r / 32) * 4 + (k / 32) % 4.  sfa: weights
@@ -76,9 +80,7 @@ struct GemmParams {
 };
 
 // Host launcher (gemm_tc.cu). Returns cudaError_t as int.
+int gemm_tc_max_splitk(int bn, int epi, int stages);
 int launch_gemm_tc(const GemmParams& p, const void* w, const void* x, int bn, cudaStream_t stream);
-// Persistent stream-K variant (gemm_sk.cu), bn <= 64. Returns -5 when the problem does not fit its workspace.
-int launch_gemm_sk(const GemmParams& p, const void* w, const void* x, int bn, cudaStream_t stream);
-int gemm_sk_init();
 
 }  // namespace b2b

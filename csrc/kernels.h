@@ -50,7 +50,7 @@ int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* 
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s);
 
 // gemm_tc.cu
-int gemm_tc_max_splitk(int bn, int epi);
+int gemm_tc_max_splitk(int bn, int epi, int stages);
 int gemm_tc_init();
 
 }  // namespace b2b

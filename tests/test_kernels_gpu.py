@@ -49,7 +49,7 @@ def test_gemm_all_token_tiles(bn):
 @pytest.mark.parametrize("m", [1, 16, 31])
 def test_gemm_splitk_cluster(splitk, m):
     w, x = bf(384, 2048, scale=0.05), bf(m, 2048)
-    close(ops.gemm(w, x, splitk=splitk, streamk=False), x.float() @ w.float().t())       # cluster / DSMEM kernel
+    close(ops.gemm(w, x, splitk=splitk), x.float() @ w.float().t())       # cluster / DSMEM kernel
 
 
 def test_gemm_fp32_out_and_bias():
@@ -428,34 +428,33 @@ def test_gemm_fp8_fused_rmsnorm_glu_residual():
     close(out, hmid.float() @ wd.float().t() + res.float(), rtol=8e-2, atol=8e-2)
 
 
-# ------------------------------------------------------------------- stream-K
+# ------------------------------------------------------- shapes of the decode step, L2 prefetch on / off
 @pytest.mark.parametrize("m,n,k", [(1, 128, 64), (3, 256, 4096), (32, 6144, 4096), (32, 4096, 14336), (17, 28672, 1024),
                                    (64, 1024, 8192), (40, 384, 640)])
-def test_gemm_streamk_matches_cluster_kernel(m, n, k):
-    """persistent stream-K kernel (tiles cut across CTAs, fp32 partials through the L2 workspace) vs fp32 reference"""
+@pytest.mark.parametrize("pf", [0, 4, 64])
+def test_gemm_decode_shapes_l2_prefetch(m, n, k, pf):
+    """cluster split-K kernel on the Llama decode shapes; the L2 weight prefetch (any distance, including far past
+    the end of the CTA's K range) must not change the result"""
     w, x = bf(n, k, scale=0.03), bf(m, k)
     ref = x.float() @ w.float().t()
-    out_sk = ops.gemm(w, x, streamk=True)
-    close(out_sk, ref)
-    out_sk2 = ops.gemm(w, x, streamk=True)          # counters self-reset: second launch identical
-    assert torch.equal(out_sk, out_sk2)
-    close(ops.gemm(w, x, streamk=False), ref)
+    out = ops.gemm(w, x, pf=pf)
+    close(out, ref)
+    assert torch.equal(out, ops.gemm(w, x, pf=pf))     # handoff counters / barriers self-reset
 
 
-@pytest.mark.parametrize("streamk", [True, False])
-def test_gemm_epilogues_both_kernels(streamk):
+def test_gemm_fused_epilogues_chain():
     h, f, m = 1024, 512, 24
     x, gamma = bf(m, h, scale=2.0), (1 + 0.1 * torch.randn(h, device="cuda")).to(torch.bfloat16)
     wg, wu = bf(f, h, scale=0.05, seed=1), bf(f, h, scale=0.05, seed=2)
     wgu = ops.fold_gamma(ops.glu_interleave_rows(wg, wu), gamma)
-    out = ops.gemm(wgu, x, epi=ops.EPI_GLU, norm_from_x=True, eps=1e-5, streamk=streamk)
+    out = ops.gemm(wgu, x, epi=ops.EPI_GLU, norm_from_x=True, eps=1e-5)
     xn = torch_ref.rms_norm(x.float(), gamma.float(), 1e-5, False)
     close(out, torch.nn.functional.silu(xn @ wg.float().t()) * (xn @ wu.float().t()), rtol=3e-2, atol=3e-2)
     wd, res = bf(256, f, scale=0.05, seed=3), bf(m, 256)
-    out2 = ops.gemm(wd, out, epi=ops.EPI_RESIDUAL, residual=res, streamk=streamk)
+    out2 = ops.gemm(wd, out, epi=ops.EPI_RESIDUAL, residual=res)
     close(out2, out.float() @ wd.float().t() + res.float())
     bias = torch.randn(256, device="cuda") * 0.1
-    close(ops.gemm(wd, out, epi=ops.EPI_GELU, bias=bias, streamk=streamk),
+    close(ops.gemm(wd, out, epi=ops.EPI_GELU, bias=bias),
           torch_ref.gelu_tanh(out.float() @ wd.float().t() + bias))
 
 
