@@ -240,7 +240,7 @@ def test_split_k_heuristic_matches_the_measured_optimum():
 
     from bee2bee_b200 import ops
 
-    fake = mock.Mock(gemm_max_splitk=lambda bn, epi: 8)
+    fake = mock.Mock(gemm_max_splitk=lambda bn, epi, stages=0: 8)
     shapes = dict(qkv=(6144, 4096), o=(4096, 4096), gu=(28672, 4096), down=(4096, 14336), head=(128256, 4096))
     with mock.patch.object(ops, "native", lambda: fake):
         pick = lambda bn, m: {k: ops.pick_splitk(n, m, kk, bn, 0) for k, (n, kk) in shapes.items()}
