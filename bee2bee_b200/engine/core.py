@@ -55,6 +55,7 @@ class Request:
     t_first: float = 0.0
     t_done: float = 0.0
     consumed: int = 0          # tokens already taken from the history ring
+    cancelled: bool = False    # set by Engine.cancel(): retired at the next burst boundary
 
     @property
     def ttft_ms(self) -> float:
@@ -189,6 +190,7 @@ class Engine:
         self._running: Dict[int, Request] = {}
         self._free_slots = list(range(max_batch - 1, -1, -1))
         self._lock = threading.Lock()
+        self._cancelled: List[int] = []            # rids cancelled since the last step (rank 0 -> plan broadcast)
         self._wake = threading.Event()
         self._stop = False
         self._thread: Optional[threading.Thread] = None
@@ -217,6 +219,18 @@ class Engine:
             while not all(r.done.is_set() for r in reqs):
                 self.step()
         return [r.wait().out_ids for r in reqs]
+
+    def cancel(self, req: Request, reason: str = "cancelled") -> None:
+        """Abandon a request (client disconnected, stop word hit, wait timed out): it stops occupying its batch slot
+        and KV pages at the next burst boundary instead of decoding to ``max_new_tokens``.  Thread-safe; on a serving
+        mesh the cancellation travels to the follower ranks with the next plan broadcast.  The reference leaks its
+        generate thread in the same situation (/root/reference/bee2bee/hf.py:107-136)."""
+        if req.done.is_set():
+            return
+        req.cancelled = True          # retired (finish_reason "cancelled") at the next burst boundary, on every rank
+        with self._lock:
+            self._cancelled.append(req.rid)
+        self._wake.set()
 
     def start(self) -> None:
         if self._thread is None:
@@ -266,7 +280,7 @@ class Engine:
                 self._wake.wait(0.05)
                 self._wake.clear()
 
-    def _sync_plan(self, fresh: List[Request]) -> Optional[List[Request]]:
+    def _sync_plan(self, fresh: List[Request], cancelled: Optional[List[int]] = None) -> Optional[List[Request]]:
         """Replicated control plane: rank 0 broadcasts the requests that arrived since the last step
         (ids, prompt, sampling params); followers materialise mirror Request objects so that every
         rank takes identical admission / retirement decisions.  Returns None once rank 0 shuts down."""
@@ -274,12 +288,14 @@ class Engine:
 
         box = [None]
         if self.rank == 0:
-            box[0] = {"stop": self._stop, "new": [(r.rid, r.prompt_ids, dict(r.params.__dict__)) for r in fresh]}
+            box[0] = {"stop": self._stop, "new": [(r.rid, r.prompt_ids, dict(r.params.__dict__)) for r in fresh],
+                      "cancel": list(cancelled or [])}
         dist.broadcast_object_list(box, src=0, group=self.plan_group)
         plan = box[0]
         if plan["stop"]:
             self._stop = True
             return None
+        self._plan_cancel = list(plan.get("cancel") or [])
         if self.rank == 0:
             return fresh
         out = []
@@ -297,6 +313,7 @@ class Engine:
     def _fail_all(self, msg: str) -> None:
         for r in list(self._running.values()) + self._pending:
             r.error = msg
+            r.t_done = time.time()
             r.done.set()
         try:
             self.runner.release(list(self._running.keys()))
@@ -309,7 +326,8 @@ class Engine:
         self._pending.clear()
 
     def step(self) -> bool:
-        """One scheduler iteration: admit + prefill, then one decode burst. Returns False when idle."""
+        """One scheduler iteration: retire cancelled requests, admit + prefill, then one decode burst.
+        Returns False when idle."""
         from .runner import SeqInit
 
         t0 = time.time()
@@ -319,11 +337,16 @@ class Engine:
                 fresh.append(self._waiting.get_nowait())
             except queue.Empty:
                 break
+        with self._lock:
+            cancelled, self._cancelled = self._cancelled, []
         if self.world > 1 and self.plan_sync:
-            fresh = self._sync_plan(fresh)
+            fresh = self._sync_plan(fresh, cancelled)
             if fresh is None:
                 return False
+            cancelled = self._plan_cancel
         self._pending.extend(fresh)
+        if cancelled:
+            self._retire_cancelled(set(cancelled))
         admitted: List[Request] = []
         still: List[Request] = []
         for r in self._pending:
@@ -343,57 +366,80 @@ class Engine:
                     for r in admitted]
             from ..utils.tracing import TRACER
             th = time.perf_counter()
-            with TRACER.range(f"prefill[{len(seqs)} seqs]", getattr(self.runner, "stream", None),
-                              device_timed=self.gpu):
-                self.runner.prefill(seqs)
-            self.host_ms["prefill"] += (time.perf_counter() - th) * 1e3
+            # the admitted requests are "running" from here on, so that a failing prefill is cleaned up by
+            # _fail_all (slots, pages, waiters) instead of leaking them
             for r in admitted:
                 self._running[r.slot] = r
+            try:
+                with TRACER.range(f"prefill[{len(seqs)} seqs]", getattr(self.runner, "stream", None),
+                                  device_timed=self.gpu):
+                    self.runner.prefill(seqs)
+            except Exception as e:
+                self._fail_all(f"prefill failed: {e!r}")
+                raise
+            self.host_ms["prefill"] += (time.perf_counter() - th) * 1e3
+            for r in admitted:
                 self.stats["prefill_tokens"] += len(r.prompt_ids)
                 self.stats["requests"] += 1
             self._collect(first=True)
         if not self._running:
             if admitted:
                 self.stats["busy_s"] += time.time() - t0
-            return bool(admitted)
+            return bool(admitted) or bool(cancelled)
         remaining = min(r.params.max_new_tokens - len(r.out_ids) for r in self._running.values())
-        n = max(1, min(self.decode_burst, remaining))
+        n = max(1, min(self.decode_burst, remaining, getattr(self.runner, "hist_len", 1 << 30)))
         th = time.perf_counter()
         self.runner.decode(n)
-        self.runner.sync()
         tc = time.perf_counter()
         self.host_ms["decode"] += (tc - th) * 1e3
         self.stats["steps"] += n
-        self._collect(steps=n)
+        self._collect(steps=n)          # blocks on the device-side "burst complete on every rank" condition
         self.host_ms["collect"] += (time.perf_counter() - tc) * 1e3
         self.stats["busy_s"] += time.time() - t0
         return True
 
-    def _fetch_window(self, width: int) -> torch.Tensor:
-        """[max_batch, width] newest tokens of every slot, starting at each request's read cursor.
-        On a multi-rank mesh the ring lives on rank 0 and the window is broadcast so that every rank
-        takes identical scheduling decisions (replicated control plane)."""
-        dev = self.device
-        cur = torch.zeros(self.max_batch, dtype=torch.int64)
+    def _retire_cancelled(self, rids) -> None:
+        """Burst boundary (the device is idle): drop cancelled requests from the queue / free their slot + pages."""
+        keep = []
+        for r in self._pending:
+            if r.rid in rids:
+                r.cancelled = True
+                r.finish_reason = r.finish_reason or "cancelled"
+                r.t_done = time.time()
+                r.done.set()
+            else:
+                keep.append(r)
+        self._pending = keep
+        gone = [b for b, r in self._running.items() if r.rid in rids]
+        if gone:
+            self.runner.release(gone)
+            for b in gone:
+                r = self._running.pop(b)
+                self.alloc.release(b)
+                self._free_slots.append(b)
+                r.cancelled = True
+                r.finish_reason = r.finish_reason or "cancelled"
+                r.t_done = time.time()
+                r.done.set()
+            self.stats["cancelled"] = self.stats.get("cancelled", 0) + len(gone)
+
+    def _fetch_window(self, width: int, first: bool = False) -> torch.Tensor:
+        """[max_batch, width] newest tokens of every slot, starting at each request's read cursor.  One kernel on
+        every rank (runner.fetch_window): it waits on rank 0's sampler / prefill flags and gathers from rank 0's ring
+        -- follower ranks read both through their NVLink mapping -- so every rank sees the same tokens and takes the
+        same scheduling decisions without a broadcast."""
+        cur = [0] * self.max_batch
         for b, r in self._running.items():
             cur[b] = r.consumed
-        idx = (cur[:, None] + torch.arange(width)[None, :]).clamp_(max=self.runner.hist_len - 1).to(dev)
-        self.h2d_bytes += idx.numel() * 8
-        if self.rank == 0:
-            win = self.runner.history.long().gather(1, idx).int()
-        else:
-            win = torch.zeros((self.max_batch, width), device=dev, dtype=torch.int32)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.broadcast(win, src=0, group=self.control_group)
+        win = self.runner.fetch_window(cur, width, first=first)      # the runner counts the cursor / wait-list bytes
         self.d2h_bytes += win.numel() * 4
-        return win.cpu()
+        return win
 
     def _collect(self, first: bool = False, steps: int = 0) -> None:
         """Pull freshly produced tokens for every running request, stream them, retire finished ones."""
         width = 1 if first else steps
         if self.gpu:
-            win = self._fetch_window(width)
+            win = self._fetch_window(width, first=first)
         finished: List[int] = []
         for b, r in list(self._running.items()):
             have = 1 if first and r.consumed == 0 else steps
@@ -410,7 +456,7 @@ class Engine:
                         self._ttfts.append((r.t_first - r.t_submit) * 1e3)
                 r.out_ids.append(int(tok))
                 self.stats["tokens"] += 1
-                if r.on_token is not None:
+                if r.on_token is not None and not r.cancelled:
                     try:
                         r.on_token(int(tok))
                     except Exception:

@@ -102,7 +102,12 @@ def generate_text(model: LoadedModel, tokenizer, device: str, prompt: str, max_n
     prompt + completion like the reference (hf.py:35-44)."""
     ids = tokenizer.encode(prompt)
     sp = SamplingParams(max_new_tokens=max_new_tokens, temperature=temperature, top_p=1.0, repetition_penalty=1.0)
-    req = model.engine.submit(ids, sp).wait(timeout=600)
+    req = model.engine.submit(ids, sp)
+    try:
+        req.wait(timeout=600)
+    except TimeoutError:
+        model.engine.cancel(req, "timeout")      # do not leave a zombie decoding to max_new_tokens
+        raise
     text = tokenizer.decode(req.out_ids)
     full = (prompt + text) if return_full_text else text
     return (full, req.out_ids) if return_ids else full
@@ -122,23 +127,29 @@ def generate_text_stream(model: LoadedModel, tokenizer, device: str, prompt: str
     sp = SamplingParams(max_new_tokens=max_new_tokens, temperature=temperature, top_p=0.95, repetition_penalty=1.15)
     req = model.engine.submit(ids, sp, on_token=q.put)
     emitted, toks = "", []
-    while True:
-        try:
-            tok = q.get(timeout=0.05)
-        except queue.Empty:
-            if req.done.is_set() and q.empty():
+    try:
+        while True:
+            try:
+                tok = q.get(timeout=0.05)
+            except queue.Empty:
+                if req.done.is_set() and q.empty():
+                    break
+                continue
+            toks.append(tok)
+            text = tokenizer.decode(toks)
+            if text.endswith("�"):
+                continue                      # incomplete multi-byte sequence: wait for more ids
+            visible, hit = cut_at_stop_words(text, STOP_WORDS)
+            if len(visible) > len(emitted):
+                yield visible[len(emitted):]
+                emitted = visible
+            if hit:
                 break
-            continue
-        toks.append(tok)
-        text = tokenizer.decode(toks)
-        if text.endswith("�"):
-            continue                      # incomplete multi-byte sequence: wait for more ids
-        visible, hit = cut_at_stop_words(text, STOP_WORDS)
-        if len(visible) > len(emitted):
-            yield visible[len(emitted):]
-            emitted = visible
-        if hit:
-            break
+    finally:
+        # stop word hit, or the consumer closed the generator (client disconnect): free the batch slot and the
+        # KV pages at the next burst boundary instead of decoding up to max_new_tokens (2048 from /chat)
+        if not req.done.is_set():
+            model.engine.cancel(req, "stop")
     if req.error:
         raise RuntimeError(req.error)
 

@@ -182,6 +182,11 @@ PRESETS: Dict[str, ModelConfig] = {
                                final_softcap=30.0, query_scale=256 ** -0.5, post_norms=True, gemma_norm=True,
                                embed_scale=16.0, eos_token_id=1, bos_token_id=0),
     "tiny-gpt2": _gpt2("tiny-gpt2", 4, 128, 2),
+    # Llama-3-8B layer shapes (hidden 4096, GQA 32:8, FFN 14336), 8 layers, small vocabulary: multi-GPU correctness
+    # tests at the real GEMM / handoff tile shapes without 16 GB of weights
+    "mini-llama-4096": ModelConfig(name="mini-llama-4096", family="llama", vocab_size=32000, hidden_size=4096,
+                                   n_layers=8, n_heads=32, n_kv_heads=8, head_dim=128, ffn_size=14336,
+                                   rope_theta=500000.0, eos_token_id=1, bos_token_id=0),
 }
 PRESETS["tiny-gpt2"].vocab_size = 384
 PRESETS["tiny-gpt2"].eos_token_id = 1

@@ -45,6 +45,7 @@ class Handoff:
     out_epoch: int = 0       # u32: number of outputs already published (local)
     out_free: int = 0        # u32: downstream acks land here (local)
     done: int = 0            # u32 scratch counter (local)
+    free_lag: int = 0        # payloads that may be outstanding on the output slot (1 = double-buffered staging)
 
 
 @dataclass
@@ -214,6 +215,13 @@ class NativePiece:
     def weight_bytes(self) -> int:
         return sum(v.numel() * v.element_size() for v in self.w.values())
 
+    def streamed_weight_bytes(self) -> int:
+        """Bytes a decode step actually streams from this piece's weights: everything except the embedding tables,
+        of which a step only gathers one row per sequence (weight_bytes() overstated the roofline)."""
+        skip = {"embed", "pos_embed"}
+        n = sum(v.numel() * v.element_size() for k, v in self.w.items() if k not in skip)
+        return n + sum(v.numel() * v.element_size() for v in self.wscale.values())
+
     def _use_inline_rstd(self, T: int) -> bool:
         return T <= 64
 
@@ -252,7 +260,7 @@ class NativePiece:
             if is_tail and hand.out_x:
                 tail_kw = dict(out_ptr=hand.out_x, ld_out=c.hidden_size, signal_flag=hand.out_flag,
                                signal_epoch=hand.out_epoch, done_counter=hand.done, free_flag=hand.out_free,
-                               bump_epoch=hand.in_epoch, ack_flag=hand.up_ack)
+                               bump_epoch=hand.in_epoch, ack_flag=hand.up_ack, free_lag=hand.free_lag)
             elif is_tail and out_x is not None:
                 tail_kw = dict(out_ptr=out_x.data_ptr(), ld_out=c.hidden_size)
             # ---------------- attention block
@@ -327,7 +335,7 @@ class NativePiece:
                 if is_tail and hand.out_x:
                     dst = ops.native().tensor_from_ptr(hand.out_x, [T, c.hidden_size], "bf16", self.device.index)
                     if hand.out_free:
-                        ops.native().flag_wait(hand.out_free, hand.out_epoch, 0)    # back-pressure
+                        ops.native().flag_wait(hand.out_free, hand.out_epoch, -hand.free_lag)    # back-pressure
                     ops.rmsnorm(d, self.w[p + "post_ffn_w"], out=dst, residual=x2, eps=eps, plus_one=c.gemma_norm)
                     ops.native().flag_signal(hand.out_flag, hand.out_epoch, hand.in_epoch, hand.up_ack)
                     xn = dst

@@ -144,7 +144,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
          dbg: int = 0, w_scale: Optional[torch.Tensor] = None,
          sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1, pf: int = -1,
-         stages: int = -1) -> Optional[torch.Tensor]:
+         stages: int = -1, free_lag: int = 0) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -176,7 +176,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
                   ack_flag, dbg, w_scale, sfa, sfb, GEMM_MC if mc < 0 else mc,
-                  L2_PREFETCH if pf < 0 else pf, stages)
+                  L2_PREFETCH if pf < 0 else pf, stages, free_lag)
     return out
 
 
@@ -322,10 +322,11 @@ def get_attn_tc_min_q() -> int:
 # ---------------------------------------------------------------------- sampler
 def sample(logits, out_tokens, *, seen=None, temperature=None, top_p=None, rep_penalty=None, seeds=None, step=None,
            peer_tokens=0, history=0, hist_pos=None, hist_stride=0, signal_flag=0, signal_epoch=0, done_counter=0,
-           vocab=0, softcap=0.0, row_base=0):
+           vocab=0, softcap=0.0, row_map=0):
+    """``row_map``: device address of int32 [rows of logits] mapping each logits row to its batch row (< 0 = skip)."""
     native().sample(logits, seen, out_tokens, peer_tokens, history, hist_pos, hist_stride, vocab, softcap,
                     temperature, top_p,
-                    rep_penalty, seeds, step, signal_flag, signal_epoch, done_counter, row_base)
+                    rep_penalty, seeds, step, signal_flag, signal_epoch, done_counter, row_map)
     return out_tokens
 
 

@@ -23,8 +23,10 @@ import torch
 from .. import ops
 from ..models.native import Handoff
 
-FLAG_WORDS = 16          # u32 slots per group (64 B, one line per group)
+FLAG_WORDS = 16          # u32 slots per channel (64 B, one line per channel)
 F_IN_FLAG, F_IN_EPOCH, F_OUT_EPOCH, F_OUT_FREE, F_DONE, F_TOK_DONE = 0, 1, 2, 3, 4, 5
+# misc channel (index groups + 1): prefill completion, published by the last rank on rank 0
+M_PF_FLAG, M_PF_EPOCH, M_PF_SEEN = 0, 1, 2
 
 
 @dataclass
@@ -59,8 +61,9 @@ class MeshComm:
     # ------------------------------------------------------------------ set-up
     def _sizes(self) -> Dict[str, int]:
         return {
-            "stage": self.groups * self.max_tokens * self.hidden * 2,           # bf16 staging per group
-            "flags": self.groups * FLAG_WORDS * 4,
+            "stage": self.groups * self.group_batch * self.hidden * 2,          # decode: one bf16 slot per group
+            "stage_pf": 2 * self.max_tokens * self.hidden * 2,                  # prefill chunks: double-buffered
+            "flags": (self.groups + 2) * FLAG_WORDS * 4,                        # groups, prefill channel, misc
             "tok": self.groups * self.group_batch * 4,                          # sampled-token return buffer (rank 0)
             "hist": self.groups * self.group_batch * self.hist_len * 4,         # token history ring (rank 0)
         }
@@ -95,27 +98,35 @@ class MeshComm:
         self.remote_prev = open_all(self.prev_rank) if self.prev_rank != self.next_rank else self.remote_next
         self.remote_first = self.remote_next if self.next_rank == 0 else (
             self.remote_prev if self.prev_rank == 0 else open_all(0))
-        dist.barrier(group=self.control_group)
+        self.init_flags()
 
     # ------------------------------------------------------------------ endpoints
     def _flag(self, table: Dict[str, int], group: int, word: int) -> int:
         return table["flags"] + (group * FLAG_WORDS + word) * 4
 
+    @property
+    def pf_channel(self) -> int:
+        return self.groups
+
+    @property
+    def misc_channel(self) -> int:
+        return self.groups + 1
+
     def handoff(self, group: int) -> Handoff:
-        """Addresses for micro-batch group ``group`` on this rank (all zero for world == 1)."""
+        """Decode endpoints of micro-batch group ``group`` on this rank (all zero for world == 1).  One staging slot
+        per group and no back-pressure flags: a group's step k+1 cannot reach a piece before the token loop has
+        carried step k through every piece behind it."""
         if self.world == 1:
             return Handoff()
         first, last = self.rank == 0, self.rank == self.world - 1
-        stage_off = group * self.max_tokens * self.hidden * 2
+        stage_off = group * self.group_batch * self.hidden * 2
         tok_off = group * self.group_batch * 4
         h = Handoff()
         h.in_flag = self._flag(self.local, group, F_IN_FLAG)
         h.in_epoch = self._flag(self.local, group, F_IN_EPOCH)
         h.out_epoch = self._flag(self.local, group, F_OUT_EPOCH)
-        h.out_free = 0                                   # decode: implied by the token loop (see DESIGN.md)
         h.done = self._flag(self.local, group, F_DONE)
         h.in_x = (self.local["tok"] + tok_off) if first else (self.local["stage"] + stage_off)
-        h.up_ack = 0
         if last:
             h.out_x = self.remote_first["tok"] + tok_off
             h.out_flag = self._flag(self.remote_first, group, F_IN_FLAG)
@@ -123,6 +134,54 @@ class MeshComm:
             h.out_x = self.remote_next["stage"] + stage_off
             h.out_flag = self._flag(self.remote_next, group, F_IN_FLAG)
         return h
+
+    def handoff_prefill(self, parity: int) -> Handoff:
+        """Prefill-chunk endpoints (own channel, staging double-buffered by chunk parity).  Chunks have no loop
+        dependency, so the slot is flow-controlled on the device: the producer's tail GEMM waits until the consumer
+        has released payload n-2 before it stores payload n (``free_lag`` = 1), the consumer's tail GEMM (last piece:
+        a flag kernel) bumps its input epoch and acks the upstream producer."""
+        if self.world == 1:
+            return Handoff()
+        first, last = self.rank == 0, self.rank == self.world - 1
+        c = self.pf_channel
+        off = parity * self.max_tokens * self.hidden * 2
+        h = Handoff()
+        h.done = self._flag(self.local, c, F_DONE)
+        h.free_lag = 1
+        if not first:
+            h.in_x = self.local["stage_pf"] + off
+            h.in_flag = self._flag(self.local, c, F_IN_FLAG)
+            h.in_epoch = self._flag(self.local, c, F_IN_EPOCH)
+            h.up_ack = self._flag(self.remote_prev, c, F_OUT_FREE)
+        if not last:
+            h.out_x = self.remote_next["stage_pf"] + off
+            h.out_flag = self._flag(self.remote_next, c, F_IN_FLAG)
+            h.out_epoch = self._flag(self.local, c, F_OUT_EPOCH)
+            h.out_free = self._flag(self.local, c, F_OUT_FREE)
+        return h
+
+    # prefill completion: the last rank publishes "first tokens of prefill #n are in rank 0's ring"
+    def pf_done_signal(self):
+        """(remote flag on rank 0, local epoch) for the last rank's flag_signal after a prefill."""
+        return (self._flag(self.remote_first, self.misc_channel, M_PF_FLAG),
+                self._flag(self.local, self.misc_channel, M_PF_EPOCH))
+
+    def pf_done_flag(self) -> int:
+        """Address of rank 0's prefill-completion counter as seen from this rank."""
+        table = self.local if self.rank == 0 else self.remote_first
+        return self._flag(table, self.misc_channel, M_PF_FLAG)
+
+    def tok_flag(self, group: int) -> int:
+        """Address of rank 0's token flag of ``group`` (1 + decode steps published by the sampler) from this rank."""
+        table = self.local if self.rank == 0 else self.remote_first
+        return self._flag(table, group, F_IN_FLAG)
+
+    def hist_base(self) -> int:
+        """Rank 0's history ring [max_batch, hist_len] as seen from this rank."""
+        return (self.local if self.rank == 0 else self.remote_first)["hist"]
+
+    def tok_base(self) -> int:
+        return (self.local if self.rank == 0 else self.remote_first)["tok"]
 
     def history_ptr(self, group: int) -> int:
         """Where the sampler of the last rank writes token history (rank 0's ring)."""
@@ -132,17 +191,20 @@ class MeshComm:
     def local_view(self, name: str, shape, dtype: str) -> torch.Tensor:
         return self.C.tensor_from_ptr(self.local[name], list(shape), dtype, self.device.index)
 
-    def reset_flags(self, token_ready: bool = True) -> None:
-        """Between bursts (GPU idle, host barrier on both sides): zero all local flags; on rank 0
-        mark the token buffer as already produced once (it was filled by prefill / last burst)."""
+    def init_flags(self) -> None:
+        """Once, before the first kernel: every counter is a monotonic epoch and is never reset afterwards.  Rank 0's
+        token flags start at 1 ("the tokens of step 0 are there": prefill writes them) and so does the last rank's
+        count of published token sets."""
         if self.world == 1:
             return
-        flags = self.local_view("flags", (self.groups, FLAG_WORDS), "i32")
+        flags = self.local_view("flags", (self.groups + 2, FLAG_WORDS), "i32")
         flags.zero_()
-        if self.rank == 0 and token_ready:
-            flags[:, F_IN_FLAG] = 1
-        if self.rank == self.world - 1 and token_ready:
-            flags[:, F_OUT_EPOCH] = 1
+        if self.rank == 0:
+            flags[:self.groups, F_IN_FLAG] = 1
+        if self.rank == self.world - 1:
+            flags[:self.groups, F_OUT_EPOCH] = 1
+        torch.cuda.synchronize(self.device)
+        self.barrier()
 
     def barrier(self) -> None:
         if self.world > 1:

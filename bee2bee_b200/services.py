@@ -193,16 +193,20 @@ class EmbeddedOllama:
         toks: List[int] = []
         sent = ""
         stream = bool(payload.get("stream", True))
-        while not (req.done.is_set() and q.empty()):
-            try:
-                toks.append(q.get(timeout=0.05))
-            except _q.Empty:
-                continue
-            if stream:
-                text = self._tok.decode(toks)
-                if len(text) > len(sent) and not text.endswith("�"):
-                    yield {"model": payload.get("model"), "response": text[len(sent):], "done": False}
-                    sent = text
+        try:
+            while not (req.done.is_set() and q.empty()):
+                try:
+                    toks.append(q.get(timeout=0.05))
+                except _q.Empty:
+                    continue
+                if stream:
+                    text = self._tok.decode(toks)
+                    if len(text) > len(sent) and not text.endswith("�"):
+                        yield {"model": payload.get("model"), "response": text[len(sent):], "done": False}
+                        sent = text
+        finally:
+            if not req.done.is_set():          # consumer went away mid-stream
+                lm.engine.cancel(req, "client_disconnect")
         text = self._tok.decode(toks)
         final = {"model": payload.get("model"), "response": "" if stream else text, "done": True,
                  "eval_count": len(toks), "prompt_eval_count": len(ids), "total_duration": int((time.time() - t0) * 1e9)}

@@ -46,7 +46,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
           int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale,
-          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages) {
+          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages, int64_t free_lag) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
@@ -112,6 +112,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.free_flag = as_ptr<const uint32_t>(free_flag);
   p.bump_epoch = as_ptr<uint32_t>(bump_epoch);
   p.ack_flag = as_ptr<uint32_t>(ack_flag);
+  p.free_lag = static_cast<uint32_t>(free_lag);
   p.dbg = as_ptr<unsigned long long>(dbg);
   if (p.epi == b2b::EPI_QKV_ROPE) {
     TORCH_CHECK(p.q_out && p.k_cache && p.v_cache && p.slots, "qkv epilogue needs q_out/k_cache/v_cache/slots");
@@ -290,7 +291,7 @@ void sample(const Tensor& logits, const OptT& seen, const Tensor& out_tokens, in
             int64_t history, const OptT& hist_pos, int64_t hist_stride, int64_t vocab, double softcap,
             const OptT& temperature, const OptT& top_p,
             const OptT& rep_penalty, const OptT& seeds, const OptT& step, int64_t signal_flag, int64_t signal_epoch,
-            int64_t done_counter, int64_t row_base) {
+            int64_t done_counter, int64_t row_map) {
   TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.stride(1) == 1, "logits: fp32");
   c10::cuda::CUDAGuard guard(logits.device());
   int* hp = ptr_or_null<int>(hist_pos);
@@ -302,17 +303,27 @@ void sample(const Tensor& logits, const OptT& seen, const Tensor& out_tokens, in
                            ptr_or_null<const float>(temperature), ptr_or_null<const float>(top_p),
                            ptr_or_null<const float>(rep_penalty), ptr_or_null<const uint32_t>(seeds),
                            ptr_or_null<const uint32_t>(step), as_ptr<uint32_t>(signal_flag),
-                           as_ptr<uint32_t>(signal_epoch), as_ptr<uint32_t>(done_counter), as_ptr<const int>(row_base),
+                           as_ptr<uint32_t>(signal_epoch), as_ptr<uint32_t>(done_counter), as_ptr<const int>(row_map),
                            cur_stream()),
         "sample");
 }
 
-void set_decode_state(const Tensor& positions, const Tensor& kv_len, const Tensor& q_len, int64_t row, int64_t kvlen) {
+void set_decode_state(const Tensor& positions, const Tensor& kv_len, const Tensor& q_len, int64_t row_map, int64_t kvlen,
+                      int64_t n) {
   c10::cuda::CUDAGuard guard(positions.device());
   check(b2b::launch_set_decode_state(reinterpret_cast<int*>(positions.data_ptr()), reinterpret_cast<int*>(kv_len.data_ptr()),
-                                     reinterpret_cast<int*>(q_len.data_ptr()), as_ptr<const int>(row),
-                                     as_ptr<const int>(kvlen), cur_stream()),
+                                     reinterpret_cast<int*>(q_len.data_ptr()), as_ptr<const int>(row_map),
+                                     as_ptr<const int>(kvlen), static_cast<int>(n), cur_stream()),
         "set_decode_state");
+}
+
+// history / cursors / out / waits are raw addresses: the ring may be peer memory, the rest mapped pinned host memory
+void fetch_window(int64_t history, int64_t hist_stride, int64_t cursors, int64_t rows, int64_t width, int64_t out,
+                  int64_t waits, int64_t n_waits) {
+  check(b2b::launch_fetch_window(as_ptr<const int>(history), static_cast<int>(hist_stride), as_ptr<const int>(cursors),
+                                 static_cast<int>(rows), static_cast<int>(width), as_ptr<int>(out),
+                                 as_ptr<const b2b::FlagWait>(waits), static_cast<int>(n_waits), cur_stream()),
+        "fetch_window");
 }
 
 void mark_seen(const Tensor& ids, const Tensor& seq_of, const Tensor& seen, int64_t vocab) {
@@ -395,6 +406,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sample", &sample);
   m.def("mark_seen", &mark_seen);
   m.def("set_decode_state", &set_decode_state);
+  m.def("fetch_window", &fetch_window);
   m.def("peer_alloc", &peer_alloc);
   m.def("peer_free", &peer_free);
   m.def("ipc_export", &ipc_export);

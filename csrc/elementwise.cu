@@ -322,18 +322,49 @@ __global__ void decode_advance_kernel(int* positions, int* kv_len, int* slots, c
 }
 
 // After a (graph-captured) prefill: install the decode state of the sequence in batch row *row.
-__global__ void set_decode_state_kernel(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen) {
+// row_map[i] = batch row of chunk sequence i whose prompt is complete after this chunk (< 0: skip).
+__global__ void set_decode_state_kernel(int* positions, int* kv_len, int* q_len, const int* row_map, const int* kvlen,
+                                        int n_rows) {
   pdl_launch_dependents();
   pdl_wait();
-  const int b = row[0], n = kvlen[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int b = row_map[i];
+  if (b < 0) return;
+  const int n = kvlen[i];
   positions[b] = n - 1;
   kv_len[b] = n;
   q_len[b] = 1;
 }
 
+// Token read-back for the scheduler: one launch waits for the producers (sampler flags of every micro-batch group,
+// prefill-done flag; the flags and the history ring may live on rank 0 = peer memory for follower ranks) and gathers
+// every sequence's new tokens straight into mapped pinned host memory -- no NCCL broadcast, no host barrier.
+__global__ void fetch_window_kernel(const int* history, int hist_stride, const int* cursors, int width, int* out,
+                                    const FlagWait* waits, int n_waits) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_waits; ++i) wait_flag_ge(waits[i].flag, waits[i].target);
+  }
+  __syncthreads();
+  const int b = blockIdx.x;
+  const int cur = cursors[b];
+  for (int j = threadIdx.x; j < width; j += blockDim.x)
+    out[static_cast<size_t>(b) * width + j] =
+        *reinterpret_cast<const volatile int*>(history + static_cast<size_t>(b) * hist_stride + ((cur + j) % hist_stride));
+}
+
 // ------------------------------------------------------------------ launchers
-int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen, cudaStream_t s) {
-  launch_kernel(set_decode_state_kernel, dim3(1), dim3(1), 0, s, 1, positions, kv_len, q_len, row, kvlen);
+int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row_map, const int* kvlen, int n,
+                            cudaStream_t s) {
+  launch_kernel(set_decode_state_kernel, dim3((n + 63) / 64), dim3(64), 0, s, 1, positions, kv_len, q_len, row_map, kvlen, n);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_fetch_window(const int* history, int hist_stride, const int* cursors, int rows, int width, int* out,
+                        const FlagWait* waits, int n_waits, cudaStream_t s) {
+  if (rows <= 0 || width <= 0) return 0;
+  launch_kernel(fetch_window_kernel, dim3(rows), dim3(64), 0, s, 1, history, hist_stride, cursors, width, out, waits, n_waits);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     if (p.free_flag != nullptr) {
       // back-pressure: the consumer must have drained the previous payload of this slot
       const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(p.signal_epoch);
-      wait_flag_ge(p.free_flag, e);
+      wait_flag_ge(p.free_flag, e - p.free_lag);
     }
 
     // QKV section bookkeeping (uniform per CTA)

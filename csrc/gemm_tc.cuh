@@ -71,7 +71,8 @@ struct GemmParams {
   uint32_t* signal_flag;          // peer (or local) flag
   uint32_t* signal_epoch;         // local: number of handoffs already published on this slot
   uint32_t* done_counter;         // local, self-resetting
-  const uint32_t* free_flag;      // local: consumer's ack (it has consumed `free_flag` inputs)
+  const uint32_t* free_flag;      // local: consumer's ack (it has released `*free_flag` payloads of this slot)
+  uint32_t free_lag;              // payloads that may be outstanding: 0 = single staging buffer, 1 = double-buffered
   uint32_t* bump_epoch;           // local: this piece's input-slot epoch (incremented once)
   uint32_t* ack_flag;             // peer: upstream producer's free_flag for our input slot
 

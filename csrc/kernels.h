@@ -45,8 +45,13 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
                   const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
                   const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
                   const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
-                  const int* row_base, cudaStream_t s);
-int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row, const int* kvlen, cudaStream_t s);
+                  const int* row_map, cudaStream_t s);
+int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* row_map, const int* kvlen, int n,
+                            cudaStream_t s);
+// token-window read-back: wait for up to `n_waits` (flag, target) pairs, then out[b, j] = history[b, (cursor[b] + j) % stride]
+struct FlagWait { const uint32_t* flag; uint32_t target; uint32_t pad; };
+int launch_fetch_window(const int* history, int hist_stride, const int* cursors, int rows, int width, int* out,
+                        const FlagWait* waits, int n_waits, cudaStream_t s);
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s);
 
 // gemm_tc.cu

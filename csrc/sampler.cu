@@ -47,7 +47,7 @@ struct SampleParams {
   uint32_t* signal_flag;    // peer flag (token handoff) or null
   uint32_t* signal_epoch;   // local epoch for the flag
   uint32_t* done_counter;   // local, self-resetting
-  const int* row_base;      // optional: per-sequence state lives at row *row_base + b
+  const int* row_map;       // optional [batch]: per-sequence state of logits row b lives at row row_map[b]; < 0 = skip the row
 };
 
 // logit -> (soft-cap) -> repetition penalty -> temperature
@@ -114,7 +114,27 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
   for (int i = tid; i < SBINS; i += SAMP_THREADS) { S.h1_lo[i] = 0u; S.h1_hi[i] = 0u; S.h2_lo[i] = 0u; S.h2_hi[i] = 0u; }
   pdl_wait();
 
-  const int bb = (p.row_base != nullptr ? p.row_base[0] : 0) + b;     // row of the per-sequence state
+  const int bb = (p.row_map != nullptr) ? p.row_map[b] : b;           // row of the per-sequence state
+  // the flag handoff counts one arrival per sequence (cluster), sampled or skipped
+  auto arrive = [&]() {
+    if (p.signal_flag != nullptr) {
+      __threadfence_system();
+      const uint32_t prev = atomicAdd(p.done_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence_system();
+        *p.done_counter = 0;
+        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) + 1;
+        *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) = e;
+        st_release_sys(p.signal_flag, e);
+      }
+    }
+  };
+  if (bb < 0) {
+    // padded / not-yet-complete row of a prefill chunk (cluster-uniform decision): nothing to sample
+    cluster_wait_acquire();
+    if (r == 0 && tid == 0) arrive();
+    return;
+  }
   const int V = p.vocab;
   const float* logits = p.logits + static_cast<size_t>(b) * p.ld;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
@@ -135,21 +155,12 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sample_kernel(const SamplePar
     if (seen != nullptr) atomicOr(&seen[token >> 5], 1u << (token & 31));
     if (p.history != nullptr) {
       const int pos = p.hist_pos[bb];
-      if (pos < p.hist_stride) p.history[static_cast<size_t>(bb) * p.hist_stride + pos] = token;
+      // the history is a ring: the host reads each burst's window before the writer can lap it
+      p.history[static_cast<size_t>(bb) * p.hist_stride + (pos % p.hist_stride)] = token;
       p.hist_pos_out[bb] = pos + 1;
     }
     if (p.peer_tokens != nullptr && p.peer_tokens != p.out_tokens) p.peer_tokens[bb] = token;
-    if (p.signal_flag != nullptr) {
-      __threadfence_system();
-      const uint32_t prev = atomicAdd(p.done_counter, 1u);
-      if (prev == gridDim.x - 1) {
-        __threadfence_system();
-        *p.done_counter = 0;
-        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) + 1;
-        *reinterpret_cast<volatile uint32_t*>(p.signal_epoch) = e;
-        st_release_sys(p.signal_flag, e);
-      }
-    }
+    arrive();
   };
 
   // ---- phase 1: L2 -> (soft-cap, penalty, temperature) -> shared memory; running max / argmax
@@ -434,12 +445,12 @@ int launch_sample(const float* logits, uint32_t* seen, int* out_tokens, int* pee
                   const int* hist_pos, int* hist_pos_out, int hist_stride, int batch, int vocab, int ld, float softcap,
                   const float* temperature, const float* top_p, const float* rep_penalty, const uint32_t* seeds,
                   const uint32_t* step, uint32_t* signal_flag, uint32_t* signal_epoch, uint32_t* done_counter,
-                  const int* row_base, cudaStream_t s) {
+                  const int* row_map, cudaStream_t s) {
   SampleParams p;
   p.logits = logits; p.seen = seen; p.out_tokens = out_tokens; p.peer_tokens = peer_tokens; p.history = history;
   p.hist_pos = hist_pos; p.hist_pos_out = hist_pos_out; p.hist_stride = hist_stride; p.vocab = vocab; p.ld = ld; p.softcap = softcap;
   p.temperature = temperature; p.top_p = top_p; p.rep_penalty = rep_penalty; p.seeds = seeds; p.step = step;
-  p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter; p.row_base = row_base;
+  p.signal_flag = signal_flag; p.signal_epoch = signal_epoch; p.done_counter = done_counter; p.row_map = row_map;
   // cluster size: the slice must fit in shared memory; beyond that use more SMs while the grid is below one wave
   int cs = 1;
   while (cs < MAX_CS && (vocab + cs - 1) / cs > MAX_SLICE) cs *= 2;

@@ -176,6 +176,62 @@ def test_engine_eos_stop_and_streaming_thread():
     assert got == first and req.finish_reason == "length" and req.ttft_ms > 0
 
 
+def test_engine_cancel_frees_slot_and_pages():
+    """an abandoned request (stop word / disconnect / timeout) must not decode to max_new_tokens"""
+    eng = Engine("tiny-llama", device="cpu", max_batch=1, max_seq_len=256, decode_burst=2)
+    sp = SamplingParams(max_new_tokens=200, temperature=0.0, ignore_eos=True)
+    a = eng.submit([1, 2, 3], sp)
+    b = eng.submit([4, 5], SamplingParams(max_new_tokens=3, temperature=0.0, ignore_eos=True))   # waits for the only slot
+    eng.step()
+    assert len(a.out_ids) >= 1 and not a.done.is_set() and not b.done.is_set()
+    eng.cancel(a)
+    while not b.done.is_set():
+        eng.step()
+    assert a.done.is_set() and a.finish_reason == "cancelled" and len(a.out_ids) < 20
+    assert len(b.out_ids) == 3
+    assert eng.alloc.free_pages == eng.alloc.num_pages - 1 and len(eng._free_slots) == 1
+    # cancelling a queued request removes it from the queue
+    c = eng.submit([7], sp)
+    d = eng.submit([8], sp)
+    eng.step()
+    eng.cancel(d)
+    eng.cancel(c)
+    eng.step()
+    assert c.done.is_set() and d.done.is_set() and not eng._running and not eng._pending
+    # the streaming helper cancels when its consumer walks away (generator closed)
+    from bee2bee_b200 import hf
+    lm, tok, _ = hf.load_model_and_tokenizer("tiny-llama", device="cpu")
+    gen = hf.generate_text_stream(lm, tok, "cpu", "user: hi", max_new_tokens=400, temperature=0.0)
+    next(gen)
+    gen.close()
+    import time
+    t0 = time.time()
+    while lm.engine._running and time.time() - t0 < 20:
+        time.sleep(0.05)
+    assert not lm.engine._running, "zombie request kept its slot"
+
+
+def test_engine_prefill_failure_does_not_leak_requests():
+    """admitted requests were lost (waiters hung, slot + pages leaked) when runner.prefill raised"""
+    eng = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64)
+    boom = {"n": 1}
+    real = eng.runner.prefill
+
+    def flaky(seqs):
+        if boom["n"]:
+            boom["n"] -= 1
+            raise RuntimeError("injected prefill fault")
+        return real(seqs)
+
+    eng.runner.prefill = flaky
+    r = eng.submit([1, 2, 3], SamplingParams(max_new_tokens=4, temperature=0.0, ignore_eos=True))
+    with pytest.raises(RuntimeError):
+        eng.step()
+    assert r.done.is_set() and "prefill failed" in (r.error or "")
+    assert eng.alloc.free_pages == eng.alloc.num_pages - 1 and len(eng._free_slots) == 2 and not eng._running
+    assert len(eng.generate([[1, 2, 3]], SamplingParams(max_new_tokens=4, temperature=0.0, ignore_eos=True))[0]) == 4
+
+
 def test_seeded_sampling_is_reproducible():
     sp = SamplingParams(max_new_tokens=8, temperature=0.9, seed=11, ignore_eos=True)
     a = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64).generate([[1, 2, 3]], sp)

@@ -122,7 +122,8 @@ def test_piece_fp8_close_to_oracle(name, quant):
 
 
 def test_graph_prefill_matches_eager_prefill():
-    """Single short prompts take the CUDA-graph prefill path (TTFT); results equal the eager chunked path."""
+    """Prefill chunks run as bucketed CUDA graphs (one pinned staging copy + one replay per chunk); results equal
+    the eager execution of the same chunk body.  A multi-sequence, multi-chunk batch goes through both as well."""
     cfg = resolve_config("tiny-llama")
     outs = []
     for graphs in (True, False):
@@ -134,11 +135,25 @@ def test_graph_prefill_matches_eager_prefill():
                         temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=slot)
             r.prefill([s])
             toks.append(int(r.tokens[slot]))
-        if graphs:
-            assert set(r._pf) == {16, 32, 64}
+        assert set(r._pf) == {(16, 1, 16, 0), (32, 1, 32, 0), (64, 1, 64, 0)}
+        assert all((st["graph"] is not None) == graphs for st in r._pf.values())
         r.decode(4)
         r.sync()
         hist, hp = r.read_history()
         outs.append((toks, hist[:4, :5].tolist(), hp[:4].tolist()))
+        r.close()
+    assert outs[0] == outs[1]
+    # several sequences per chunk, several chunks, one prompt spanning two chunks
+    outs = []
+    for graphs in (True, False):
+        r = GpuRunner(cfg, "", 0, 1, torch.device("cuda:0"), max_batch=8, groups=1, max_seq_len=256,
+                      max_prefill_tokens=64, seed=0, use_graphs=graphs)
+        seqs = [SeqInit(slot=b, prompt=[(5 * i + b) % cfg.vocab_size for i in range(L)], pages=[1 + 4 * b + j for j in range(4)],
+                        temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=b)
+                for b, L in enumerate((9, 30, 3, 100, 17, 64, 1, 2))]
+        r.prefill(seqs)
+        r.decode(3)
+        outs.append(r.fetch_window([0] * 8, 4).tolist())
+        assert r.pf_chunks >= 5
         r.close()
     assert outs[0] == outs[1]
