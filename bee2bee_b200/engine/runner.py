@@ -399,13 +399,24 @@ class GpuRunner:
     def _ensure_graphs(self) -> None:
         if self.graphs or not self.use_graphs:
             return
-        # multi-rank: graphs that spin on peer flags cannot be warmed up in isolation; capture without a dry run
+        # multi-rank: graphs that spin on peer flags cannot be warmed up in isolation; capture without a dry run.
+        # ONE graph holds a decode step of every group (in wavefront order): the PDL chain then also spans the group
+        # boundaries (the first kernel of group g+1 becomes resident under the tail of group g) and a step costs one
+        # graph launch instead of `groups`.  B2B_GRAPH_PER_GROUP=1 restores one graph per group.
+        per_group = os.environ.get("B2B_GRAPH_PER_GROUP", "0") == "1"
         with torch.cuda.stream(self.stream):
-            for g in range(self.groups):
+            if per_group:
+                for g in range(self.groups):
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
+                        self._decode_group(g)
+                    self.graphs[g] = graph
+            else:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
-                    self._decode_group(g)
-                self.graphs[g] = graph
+                    for g in range(self.groups):
+                        self._decode_group(g)
+                self.graphs[-1] = graph
         self.stream.synchronize()
 
     def warmup(self) -> None:
@@ -442,7 +453,11 @@ class GpuRunner:
 
     def _enqueue_decode(self, n_steps: int) -> None:
         with torch.cuda.stream(self.stream):
+            step_graph = self.graphs.get(-1) if self.use_graphs else None
             for _ in range(n_steps):
+                if step_graph is not None:
+                    step_graph.replay()
+                    continue
                 for g in range(self.groups):
                     if self.use_graphs:
                         self.graphs[g].replay()

@@ -15,8 +15,10 @@ def env_rank_world() -> Tuple[int, int, int]:
             int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0"))))
 
 
-def init_distributed(backend: Optional[str] = None, timeout_s: int = 600) -> Tuple[int, int, int]:
-    """Initialise from torchrun-style env vars. Returns (rank, world, local_rank)."""
+def init_distributed(backend: Optional[str] = None, timeout_s: int = 600, eager: bool = True) -> Tuple[int, int, int]:
+    """Initialise from torchrun-style env vars. Returns (rank, world, local_rank).  ``eager=False`` lets NCCL create its
+    communicators lazily: unbatched send / recv then run on dedicated per-pair communicators instead of being serialised
+    with every other op of the group (what the constructed NCCL pipeline arm wants)."""
     import torch.distributed as dist
 
     rank, world, local = env_rank_world()
@@ -30,7 +32,7 @@ def init_distributed(backend: Optional[str] = None, timeout_s: int = 600) -> Tup
         torch.cuda.set_device(local)
     if not dist.is_initialized():
         kw = {}
-        if backend == "nccl":
+        if backend == "nccl" and eager:
             kw["device_id"] = torch.device(f"cuda:{local}")
         dist.init_process_group(backend=backend, rank=rank, world_size=world,
                                 timeout=datetime.timedelta(seconds=timeout_s), **kw)

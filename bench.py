@@ -294,7 +294,8 @@ def run_nccl(args):
     from bee2bee_b200.models.config import resolve_config
     from bee2bee_b200.parallel.dist import init_distributed, max_over_ranks, shutdown
 
-    rank, world, local = init_distributed()
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+    rank, world, local = init_distributed(eager=False)       # per-pair P2P communicators: hops are not serialised
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     cfg = resolve_config(args.model)
@@ -350,6 +351,9 @@ def run_nccl(args):
     # end to end: pinned prompts -> H2D -> prefill -> K decode steps -> tokens read back once per burst of <= 64 steps
     e2e = None
     if not args.no_e2e:
+        reset_and_prefill()                 # warm pass, like the product arm's
+        pipe.decode(2)
+        pipe.finish()
         barrier_sync()
         t0 = time.perf_counter()
         reset_and_prefill()

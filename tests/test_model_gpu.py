@@ -134,6 +134,7 @@ def test_graph_prefill_matches_eager_prefill():
             s = SeqInit(slot=slot, prompt=[(3 * i + slot) % cfg.vocab_size for i in range(L)], pages=[1 + 2 * slot, 2 + 2 * slot],
                         temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=slot)
             r.prefill([s])
+            r.sync()                        # prefill only enqueues; the read-back kernel is the synchronisation point
             toks.append(int(r.tokens[slot]))
         assert set(r._pf) == {(16, 1, 16, 0), (32, 1, 32, 0), (64, 1, 64, 0)}
         assert all((st["graph"] is not None) == graphs for st in r._pf.values())
