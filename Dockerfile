@@ -6,4 +6,4 @@ RUN pip install --no-cache-dir click rich websockets psutil fastapi "uvicorn[sta
  && python -c "import __graft_entry__ as g; g.build()"
 ENV BEE2BEE_OFFLINE=1
 EXPOSE 4001 8000
-CMD ["python", "-m", "bee2bee_b200", "serve-hf", "--model", "distilgpt2", "--api-port", "8000"]
+CMD ["python", "-m", "bee2bee_b200", "serve-hf", "--random-weights", "--model", "distilgpt2", "--api-port", "8000"]

@@ -61,8 +61,11 @@ def _serve(**kw):
 @click.option("--region", default="Auto", help="Region name")
 @click.option("--api-port", default=8000, type=int, help="FastAPI port for local access")
 @click.option("--pieces", default=1, type=int, help="layer pieces (GPUs) for the embedded engine")
-def serve_ollama(model, host, port, public_host, region, api_port, pieces):
+@click.option("--random-weights", is_flag=True, help="embedded engine: allow random-init weights when no checkpoint exists")
+def serve_ollama(model, host, port, public_host, region, api_port, pieces, random_weights):
     """Serve a model with the Ollama API shape (daemon if reachable, else the embedded engine)."""
+    if random_weights:
+        os.environ["B2B_ALLOW_RANDOM_WEIGHTS"] = "1"
     _serve(host=host, port=port, bootstrap_link=get_bootstrap_url(), model_name=model, backend="ollama",
            announce_host=public_host, region=region, api_port=api_port, service_kw={"pieces": pieces})
 
@@ -75,8 +78,12 @@ def serve_ollama(model, host, port, public_host, region, api_port, pieces):
 @click.option("--pieces", default=1, type=int, help="split the model into this many layer pieces (one GPU each)")
 @click.option("--max-batch", default=None, type=int, help="concurrent sequences (continuous batching)")
 @click.option("--max-seq-len", default=None, type=int, help="context budget per sequence")
-def serve_hf(model, port, region, api_port, pieces, max_batch, max_seq_len):
+@click.option("--random-weights", is_flag=True, help="allow random-init weights when --model is not a local checkpoint "
+                                                     "directory (benchmarks / smoke tests: the node serves noise)")
+def serve_hf(model, port, region, api_port, pieces, max_batch, max_seq_len, random_weights):
     """Serve a Hugging Face model on the native engine with built-in FastAPI."""
+    if random_weights:
+        os.environ["B2B_ALLOW_RANDOM_WEIGHTS"] = "1"      # inherited by the follower ranks of --pieces N
     kw = {}
     if max_batch:
         kw["max_batch"] = max_batch

@@ -88,6 +88,13 @@ class ModelConfig:
                 norm_eps=d.get("layer_norm_epsilon", 1e-5), act="gelu_tanh", glu=False, rope_theta=0.0,
                 tie_embeddings=True, bias=True, eos_token_id=d.get("eos_token_id", 50256),
                 bos_token_id=d.get("bos_token_id", 50256))
+        # checkpoints the loader would map wrongly are rejected instead of loading "successfully" 
+        if d.get("attention_bias") or d.get("mlp_bias"):
+            raise ValueError(f"{name or mt}: attention_bias / mlp_bias checkpoints (Qwen-style) are not supported: "
+                             "the weight map carries no bias tensors for this family")
+        rs = d.get("rope_scaling")
+        if rs and (rs.get("rope_type") or rs.get("type") or "default") not in ("default",):
+            raise ValueError(f"{name or mt}: rope_scaling {rs!r} is not implemented (plain RoPE only)")
         h = d["hidden_size"]
         nh = d["num_attention_heads"]
         hd = d.get("head_dim") or h // nh

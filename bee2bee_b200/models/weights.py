@@ -223,11 +223,40 @@ def load_hf_dir(path: str, cfg: ModelConfig, layers: Iterable[int], first: bool,
     return {k: v.to(device=device, dtype=dtype).contiguous() for k, v in out.items()}
 
 
+class WeightsUnavailable(RuntimeError):
+    """No checkpoint for ``model`` and random initialisation was not asked for."""
+
+
+#: model name -> "checkpoint" | "random-init" (what the last load of that name actually used; service metadata)
+WEIGHT_SOURCE: Dict[str, str] = {}
+
+
+def random_weights_allowed(model: str) -> bool:
+    """Random initialisation is OPT-IN: the synthetic test presets, or ``B2B_ALLOW_RANDOM_WEIGHTS=1``
+    (benchmarks, smoke runs, CI -- there is no network in the build environment, hence no checkpoints).  Without it a
+    node must not announce ``llama-3-8b`` to the mesh and serve noise; the reference would fail to load instead
+    (/root/reference/bee2bee/hf.py:23-32)."""
+    name = os.path.basename(os.path.normpath(model)).lower() if model else ""
+    return name.startswith(("tiny-", "mini-")) or os.environ.get("B2B_ALLOW_RANDOM_WEIGHTS", "0") == "1"
+
+
 def load_or_init(model: str, cfg: ModelConfig, layers: Iterable[int], first: bool, last: bool, device="cpu",
                  dtype=torch.float32, seed: int = 0) -> Tensors:
     layers = list(layers)
-    if os.path.isdir(model):
+    if model and os.path.isdir(model):
         t = load_hf_dir(model, cfg, layers, first, last, device, dtype)
         if t is not None:
+            WEIGHT_SOURCE[model] = "checkpoint"
             return t
+    if model and not random_weights_allowed(model) and not random_weights_allowed(cfg.name):
+        raise WeightsUnavailable(
+            f"no safetensors checkpoint for '{model}' (not a local Hugging Face directory). Point --model at a local "
+            f"directory, or opt into random-init weights with --random-weights / B2B_ALLOW_RANDOM_WEIGHTS=1 "
+            f"(benchmarks and smoke tests only: the node would serve noise).")
+    if model:
+        if WEIGHT_SOURCE.get(model) != "random-init" and not os.path.basename(model).lower().startswith(("tiny-", "mini-")):
+            import logging
+            logging.getLogger("bee2bee_b200").warning(
+                "model '%s': RANDOM-INIT weights (no checkpoint found; allowed by B2B_ALLOW_RANDOM_WEIGHTS)", model)
+        WEIGHT_SOURCE[model] = "random-init"
     return init_random(cfg, layers, first, last, device, dtype, seed)

@@ -112,8 +112,11 @@ class HFService(BaseService):
             raise ServiceError(f"Failed to load model: {exc}")
 
     def get_metadata(self) -> Dict[str, Any]:
+        from .models.weights import WEIGHT_SOURCE
+
         return {"models": [self.model_name], "price_per_token": self.price_per_token,
-                "max_new_tokens": self.max_new_tokens, "backend": "b200-native", "pieces": self.pieces}
+                "max_new_tokens": self.max_new_tokens, "backend": "b200-native", "pieces": self.pieces,
+                "weights": WEIGHT_SOURCE.get(self.model_name, "unloaded")}
 
     def _args(self, params: Dict[str, Any]):
         prompt = params.get("prompt")

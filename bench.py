@@ -29,6 +29,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# no network -> no checkpoints: the benchmark runs the named architecture on random-init weights ("data": "synthetic")
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")
 
 # BASELINE.json "configs" (config 1 is the CPU plumbing test: tests/test_pipeline_node.py, tools/cpu_plumbing_bench.py)
 CONFIGS = {

@@ -4,6 +4,8 @@ providers, pick the cheapest one for a model and stream a generation from it.
     python -m bee2bee_b200 serve-hf --model tiny-llama --api-port 8000      # terminal 1 (prints its ws:// address)
     python examples/p2p_request_demo.py ws://127.0.0.1:<port> tiny-llama     # terminal 2
 """
+import os
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
 import asyncio
 import sys
 

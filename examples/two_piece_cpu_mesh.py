@@ -1,6 +1,8 @@
 """BASELINE.json config 1 in one file: distilgpt2 split into two layer pieces hosted by two mesh
 peers on this machine (CPU), hidden states hop over the loopback p2p runtime, generation through
 the FastAPI `/generate` route."""
+import os
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
 import asyncio
 
 import httpx

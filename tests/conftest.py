@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 
 # keep every test hermetic: private BEE2BEE_HOME, no WAN probing
 os.environ.setdefault("BEE2BEE_OFFLINE", "1")
+# no network -> no checkpoints: the suites run the real architectures on random-init weights (opt-in, see
+# models/weights.py::random_weights_allowed; test_weights_policy covers the default refusal)
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")
 
 
 def pytest_configure(config):

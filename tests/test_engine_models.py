@@ -303,3 +303,29 @@ def test_split_k_heuristic_matches_the_measured_optimum():
         assert pick(32, 32) == dict(qkv=4, o=4, gu=1, down=8, head=1)      # profiles/raw/layer_sweep_reduce_scatter.txt
         assert pick(16, 1) == dict(qkv=4, o=4, gu=1, down=4, head=1)       # >= 4 token columns per CTA of the cluster
         assert all(v == 1 for v in pick(256, 4096).values())               # prefill: tiles already fill the machine
+
+
+def test_weights_policy_random_init_is_opt_in(monkeypatch, tmp_path):
+    """`serve-hf --model llama-3-8b` must not silently serve noise"""
+    from bee2bee_b200.models.weights import WEIGHT_SOURCE, WeightsUnavailable, load_or_init
+    from bee2bee_b200.services import HFService, ServiceError
+
+    cfg = resolve_config("distilgpt2")
+    monkeypatch.setenv("B2B_ALLOW_RANDOM_WEIGHTS", "0")
+    with pytest.raises(WeightsUnavailable):
+        load_or_init("distilgpt2", cfg, range(1), True, False)
+    svc = HFService("distilgpt2", device="cpu")
+    with pytest.raises(ServiceError):
+        svc.load_sync()
+    tiny = resolve_config("tiny-llama")
+    assert "l0.wq" in load_or_init("tiny-llama", tiny, range(1), True, False)        # test presets stay usable
+    monkeypatch.setenv("B2B_ALLOW_RANDOM_WEIGHTS", "1")
+    assert "l0.wq" in load_or_init("distilgpt2", cfg, range(1), True, False)
+    assert WEIGHT_SOURCE["distilgpt2"] == "random-init"
+    # unsupported checkpoint flavours are rejected, not mis-loaded
+    from bee2bee_b200.models.config import ModelConfig
+    base = tiny.to_hf_dict()
+    with pytest.raises(ValueError):
+        ModelConfig.from_hf_dict({**base, "attention_bias": True})
+    with pytest.raises(ValueError):
+        ModelConfig.from_hf_dict({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})

@@ -6,6 +6,7 @@ import argparse
 import asyncio
 import json
 import os
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
 import statistics
 import sys
 import time

@@ -1,5 +1,6 @@
 """Llama-3-8B batch-32 decode without CUDA graphs so that ncu sees individual launches."""
 import os, sys
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bee2bee_b200.engine.runner import GpuRunner, SeqInit

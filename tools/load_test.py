@@ -3,7 +3,7 @@ N clients x R requests each, a mix of buffered and streamed generations; reports
 time to first streamed chunk, aggregate generated tokens/s (from the engine's own counters, `GET /metrics`) and
 the KV-cache page utilisation sampled while the load runs.
 
-    python -m bee2bee_b200 serve-hf --model zephyr-7b-beta --api-port 8000 &
+    python -m bee2bee_b200 serve-hf --random-weights --model zephyr-7b-beta --api-port 8000 &
     python tools/load_test.py --url http://127.0.0.1:8000 --clients 16 --requests 4 --max-new-tokens 64
 
 `--spawn MODEL` starts (and stops) the server itself.  Parity: the reference has no load tool; its sidecar serves one
@@ -140,7 +140,7 @@ def main(argv=None):
         port = free_port()
         args.url = f"http://127.0.0.1:{port}"
         env = dict(os.environ, BEE2BEE_OFFLINE="1")
-        proc = subprocess.Popen([sys.executable, "-m", "bee2bee_b200", "serve-hf", "--model", args.spawn, "--pieces", str(args.pieces),
+        proc = subprocess.Popen([sys.executable, "-m", "bee2bee_b200", "serve-hf", "--random-weights", "--model", args.spawn, "--pieces", str(args.pieces),
                                  "--api-port", str(port), "--max-batch", str(args.max_batch), "--max-seq-len", str(args.max_seq_len)],
                                 env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT, start_new_session=True)
         t0 = time.time()

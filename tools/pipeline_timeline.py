@@ -1,5 +1,7 @@
 """Per-rank timeline of the wavefront (torchrun): for each (step, group) the device time spent in the
 group's graph (spin-wait on the upstream flag + compute) and the gaps between graphs."""
+import os
+os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
