@@ -459,7 +459,9 @@ int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 template <int D>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int G, int QB,
               int seqs, int qblocks, cudaStream_t s) {
-  static const bool p_tmem = [] { const char* e = std::getenv("B2B_ATTN_P_TMEM"); return e && e[0] == '1'; }();   // experimental
+  // P in tensor memory (TS-form tcgen05.mma): validated on B200 in round 2 (same error levels, 757 vs 722 TFLOP/s at
+  // T = 4096, profiles/attention_tc.md) -> default on; B2B_ATTN_P_TMEM=0 selects the shared-memory P variant
+  static const bool p_tmem = [] { const char* e = std::getenv("B2B_ATTN_P_TMEM"); return !(e && e[0] == '0'); }();
   if (p_tmem)
     return p.softcap > 0.f ? launch_tc_cap<D, true, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s)
                            : launch_tc_cap<D, false, true>(tq, tk, tv, p, G, QB, seqs, qblocks, s);

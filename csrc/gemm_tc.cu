@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   // ------------------------------------------------------------ fused epilogue
   if (warp >= 2) {
     const int n_glob = tile_n * BM + row;
-    float* xch = red + splitk * BM * CWP;          // GLU exchange buffer [ncol][64] (behind the landing zone)
+    float* xch = red + (splitk > 1 ? splitk * BM * CWP : 0);   // GLU exchange buffer [ncol][64] (behind the landing zone, if any)
     const float bias_v = (p.bias != nullptr) ? p.bias[n_glob] : 0.f;
     // fp8: per-output-row weight scale (the per-token activation scale rides in rstd_s)
     const float wsc = (FP8 && p.w_scale != nullptr) ? p.w_scale[n_glob] : 1.f;
@@ -741,6 +741,13 @@ int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn,
     const int dflt = gemm_tc_default_stages(bn);
     if (p.stages <= 0 || p.stages > dflt) p.stages = dflt;
     if (p.stages < 2) p.stages = 2;
+  }
+  {
+    // the epilogue reuses the (by then idle) stage ring: GLU exchange buffer bn x 64 floats when there is no split-K
+    // landing zone in front of it -- a shallow ring must still hold it
+    const int stage_bytes = 128 * 128 + bn * 128;
+    const int need = (p.epi == EPI_GLU) ? bn * 256 : 0;
+    while (p.stages * stage_bytes < need && p.stages < gemm_tc_default_stages(bn)) ++p.stages;
   }
   const int smax = gemm_tc_max_splitk(bn, p.epi, p.stages);
   if (p.splitk > smax) p.splitk = smax;

@@ -485,8 +485,7 @@ def test_dense_layer_forward_backward_on_tensor_cores():
         close(gb, g.mul((zr > 0).float()).sum(0) if act == "relu" else gb, rtol=1e-3, atol=1e-3)
 
 
-# ------------------------------------------------- experimental: TMA-multicast cluster GEMM (opt-in, round-2 bring-up)
-@pytest.mark.skipif(os.environ.get("B2B_TEST_EXPERIMENTAL") != "1", reason="experimental kernel path: set B2B_TEST_EXPERIMENTAL=1")
+# ------------------------------------------------- TMA-multicast cluster GEMM (correct on hardware; not faster, so opt-in)
 @pytest.mark.parametrize("mc", [2, 4])
 @pytest.mark.parametrize("m", [512, 300])
 def test_gemm_multicast_cluster(mc, m):
@@ -498,16 +497,17 @@ def test_gemm_multicast_cluster(mc, m):
         close(ops.gemm(w, x, bn=bn, splitk=1, mc=mc, epi=ops.EPI_RESIDUAL, residual=res), ref + res.float(), rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.skipif(os.environ.get("B2B_TEST_EXPERIMENTAL") != "1", reason="experimental kernel path: set B2B_TEST_EXPERIMENTAL=1")
-def test_attention_p_in_tmem_experimental():
-    """P kept in tensor memory (TS-form tcgen05.mma): the numerics script must report the same error levels."""
+@pytest.mark.parametrize("p_tmem", ["1", "0"])
+def test_attention_p_in_tmem_and_smem_variants(p_tmem):
+    """P kept in tensor memory (TS-form tcgen05.mma, the default) and the shared-memory P variant: the numerics
+    script must report the same error levels for both."""
     import re
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "attn_tc_check.py")], capture_output=True, text=True,
-                         timeout=600, env=dict(os.environ, B2B_ATTN_P_TMEM="1"))
+                         timeout=600, env=dict(os.environ, B2B_ATTN_P_TMEM=p_tmem))
     assert out.returncode == 0, out.stderr[-2000:]
     errs = [float(x) for x in re.findall(r"max_err ([0-9.]+)", out.stdout)]
     assert len(errs) >= 5 and max(errs) < 0.03, out.stdout
