@@ -89,7 +89,22 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
-#: EXPERIMENTAL (untested on hardware in round 1, default off): cluster size of the TMA-multicast prefill GEMM (2 or 4);
+def pick_prefill_tile(n_out: int, m_tok: int):
+    """(token tile, ring depth) of a prefill GEMM (m_tok > 64), measured on B200 (profiles/prefill_gemm.md): once a GEMM
+    has more tiles than SMs, TWO resident CTAs per SM with a shallow ring beat one CTA with a deep ring -- the epilogue
+    of one tile (TMEM -> registers -> global) overlaps the main loop of the other (955 vs 787 TFLOP/s over the
+    Llama-3-8B layer at 4096 tokens, 570 vs 551 at 512).  0 = the tile's default depth."""
+    tiles256 = (n_out // 128) * ((m_tok + 255) // 256)
+    tiles128 = (n_out // 128) * ((m_tok + 127) // 128)
+    if m_tok > 256 and tiles256 > NUM_SMS:
+        return 256, 2
+    if tiles128 > NUM_SMS:
+        return 128, 3
+    return (128 if m_tok <= 512 else 256), 0
+
+
+#: cluster size of the TMA-multicast prefill GEMM (2 or 4); correct on hardware but NOT faster (the prefill GEMM is not
+#: L2-bound, profiles/prefill_gemm.md), so default off;
 #: applies to bf16 GEMMs with token tiles of 128 / 256 and no split-K, everything else ignores it
 GEMM_MC = int(os.environ.get("B2B_GEMM_MC", "0"))
 
@@ -149,7 +164,14 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
     m_tok, k = x.shape
     n_out = w.shape[0]
     if bn <= 0:
-        bn = pick_bn_mx(m_tok) if sfa is not None else pick_bn(m_tok)
+        if sfa is not None:
+            bn = pick_bn_mx(m_tok)
+        elif m_tok > 64:
+            bn, st = pick_prefill_tile(n_out, m_tok)
+            if stages < 0:
+                stages = st
+        else:
+            bn = pick_bn(m_tok)
     if stages < 0:
         stages = GEMM_STAGES if bn <= 64 else 0
     if splitk <= 0:
@@ -304,9 +326,17 @@ def add(a, b, out=None):
 
 # -------------------------------------------------------------------- attention
 def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, max_q, n_q, n_kv, head_dim,
-              window=0, softcap=0.0, splits=1, ws=None):
+              window=0, softcap=0.0, splits=1, ws=None, use_tc=-1):
+    """Paged-KV attention.  Prefill chunks (max_q >= 2) run on the tcgen05 flash kernel.  Decode (max_q == 1) also does
+    when the batch fills the machine (sequences x kv heads >= 128 CTAs) or no split-KV was asked for: measured on B200
+    (profiles/decode_attention.md) it streams the KV pages at 0.66 of the HBM peak at 8k context against 0.49 for the
+    CUDA-core split-KV kernel, and is faster even at 64 tokens (7.9 vs 10.1 us); few sequences with a long context
+    keep the split-KV kernel (more CTAs than (sequence, kv head) pairs)."""
+    if use_tc < 0 and max_q == 1:
+        seqs = q_len.shape[0]
+        use_tc = 1 if (seqs * n_kv >= 128 or splits <= 1) else 0
     native().attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, ws, max_q, n_q, n_kv, head_dim,
-                       window, softcap, splits)
+                       window, softcap, splits, use_tc)
     return out
 
 

@@ -250,12 +250,15 @@ int64_t get_attn_tc_min_q() { return g_attn_tc_min_q; }
 void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& out,
                const Tensor& block_table, const Tensor& q_start, const Tensor& q_len, const Tensor& kv_len,
                const OptT& ws, int64_t max_q, int64_t n_q, int64_t n_kv, int64_t head_dim, int64_t window,
-               double softcap, int64_t splits) {
+               double softcap, int64_t splits, int64_t use_tc) {
   check_bf16(q, "q");
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(block_table.scalar_type() == at::kInt && q_len.scalar_type() == at::kInt, "int32 metadata expected");
   const int seqs = static_cast<int>(q_len.size(0));
-  if (max_q >= g_attn_tc_min_q && g_attn_tc_min_q > 0 &&
+  // use_tc: -1 = by query-chunk length (prefill chunks), 1 = force the tcgen05 kernel (decode: one-token query blocks,
+  // the GQA group stacked into the MMA rows), 0 = force the CUDA-core kernel (split-KV decode of few sequences)
+  const bool want_tc = use_tc < 0 ? (max_q >= g_attn_tc_min_q && g_attn_tc_min_q > 0) : (use_tc > 0 && g_attn_tc_min_q > 0);
+  if (want_tc &&
       b2b::attention_tc_supported(static_cast<int>(n_q), static_cast<int>(n_kv), static_cast<int>(head_dim))) {
     // prefill chunk: tcgen05 flash attention
     check(b2b::launch_attention_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),

@@ -211,19 +211,25 @@ def _attn_ref(q, kc, vc, bt, q_lens, kv_lens, nq, nkv, hd, window, softcap):
 
 @pytest.mark.parametrize("hd,nq,nkv", [(128, 8, 2), (64, 4, 4), (256, 4, 2), (128, 32, 8)])
 @pytest.mark.parametrize("window,softcap", [(0, 0.0), (100, 50.0)])
-def test_attention_decode(hd, nq, nkv, window, softcap):
-    kv_lens = [1, 63, 64, 65, 300, 17]
+@pytest.mark.parametrize("use_tc", [1, 0])
+def test_attention_decode(hd, nq, nkv, window, softcap, use_tc):
+    """decode (one query token per sequence) on the tcgen05 flash kernel (one-token query blocks, the default) and on
+    the CUDA-core kernel; an inactive batch row (q_len 0) must be left alone by both"""
+    kv_lens = [1, 63, 64, 65, 300, 17, 1000]
     S = len(kv_lens)
     kc, vc, bt = _paged_setup(kv_lens, nkv, hd)
     q = bf(S, nq * hd, scale=0.3)
     out = torch.zeros_like(q)
     ar = torch.arange(S, device="cuda", dtype=torch.int32)
     ones = torch.ones(S, device="cuda", dtype=torch.int32)
+    ones[3] = 0                                     # inactive slot
     kvl = torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
     ops.attention(q, kc, vc, out, bt, ar, ones, kvl, max_q=1, n_q=nq, n_kv=nkv, head_dim=hd, window=window,
-                  softcap=softcap)
+                  softcap=softcap, use_tc=use_tc)
     ref = _attn_ref(q, kc, vc, bt, [1] * S, kv_lens, nq, nkv, hd, window, softcap)
-    close(out, ref)
+    keep = [i for i in range(S) if i != 3]
+    close(out[keep], ref[keep])
+    assert float(out[3].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("splits", [2, 5])
