@@ -153,13 +153,28 @@ class TaskExecutor:
 
     # ---- partitioned model: layer range [start, end) ------------------------------------------
     def _t_hf_part_load(self, p):
-        from .parallel.cpu_pipeline import PieceHost
-        from .models.config import resolve_config, split_layers
+        from .models.config import resolve_config, supports_half_layer_pieces
 
         name = p.get("model_name", "distilgpt2")
         cfg = resolve_config(name)
         start, end = int(p.get("start", 0)), int(p.get("end", cfg.n_layers))
         model_id = p.get("model_id") or new_id("hfpart")
+        device = str(p.get("device") or self.device)
+        if device.startswith("cuda") and cfg.norm == "rms" and cfg.glu:
+            # B200 data plane: the layer range runs on the hand-written kernels with a paged KV cache, and hop payloads
+            # may stay in device memory (hidden_ref: cudaMemcpyPeerAsync / CUDA IPC instead of JSON lists)
+            import torch
+            from .engine.tokenizer import load_tokenizer
+            from .parallel.gpu_piece import GpuPieceHost
+
+            if device == "cuda":
+                device = f"cuda:{torch.cuda.current_device()}"
+            host = GpuPieceHost(name, start, end, device=device, max_tokens=int(p.get("max_tokens", 512)),
+                                max_seq_len=int(p.get("max_seq_len", 1024)))
+            tok = load_tokenizer(name, cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id)
+            self.models[model_id] = {"kind": "hf_part_gpu", "host": host, "tok": tok, "cfg": cfg}
+            return {"model_id": model_id, "start": start, "end": min(end, cfg.n_layers), "device": device,
+                    "backend": "b200-native"}
         from .hf import build_layer_partial
 
         piece, tok, dev = build_layer_partial(name, start, end, device="cpu")
@@ -172,6 +187,8 @@ class TaskExecutor:
         from .parallel.cpu_pipeline import decode_tensor, encode_tensor
 
         ent = self.models.get(p.get("model_id"))
+        if ent and ent["kind"] == "hf_part_gpu":
+            return self._hf_part_forward_gpu(ent, p)
         if not ent or ent["kind"] != "hf_part":
             raise TaskError("model_not_loaded")
         piece, tok = ent["piece"], ent["tok"]
@@ -196,6 +213,41 @@ class TaskExecutor:
         if p.get("binary", False):
             return {"hidden_b64": encode_tensor(y)}
         return {"hidden": y.float().numpy().tolist()}
+
+    def _hf_part_forward_gpu(self, ent, p):
+        """hf_part_forward on a GPU-resident piece.  Input: text / ids (first piece), ``hidden_ref`` (device-resident
+        payload of the previous hop: peer copy over NVLink, same or other process), or the legacy hidden / hidden_b64
+        frames.  Output: ``hidden_ref`` when ``keep_on_device`` (the frame then carries ~100 bytes), else the legacy
+        encodings; the last piece returns the logits of the final position."""
+        import torch
+
+        from .parallel.cpu_pipeline import decode_tensor, encode_tensor
+        from .parallel.gpu_piece import release_buffer
+
+        host, tok = ent["host"], ent["tok"]
+        ids, hidden = None, None
+        if p.get("text") is not None:
+            ids = tok.encode(p["text"])
+        elif p.get("ids") is not None:
+            ids = [int(t) for t in p["ids"]]
+        elif p.get("hidden_ref") is not None:
+            hidden = host.load_hidden_ref(p["hidden_ref"])
+            if p.get("release_ref", True):
+                release_buffer(p["hidden_ref"].get("ref", ""))
+        elif p.get("hidden_b64") is not None:
+            hidden = host.load_hidden_host(decode_tensor(p["hidden_b64"]))
+        elif p.get("hidden") is not None:
+            hidden = host.load_hidden_host(torch.tensor(np.asarray(p["hidden"], dtype=np.float32)))
+        else:
+            raise TaskError("no_input")
+        res = host.forward(p.get("session"), ids=ids, hidden=hidden, pos0=p.get("pos0"),
+                           keep_on_device=bool(p.get("keep_on_device")))
+        if "hidden_ref" in res:
+            return {"hidden_ref": res["hidden_ref"]}
+        y = res["logits"][None] if "logits" in res else res["hidden"][None]          # [1, T, H] / [1, 1, V]
+        if p.get("binary", False):
+            return {"hidden_b64": encode_tensor(y.cpu())}
+        return {"hidden": y.float().cpu().numpy().tolist()}
 
     DISPATCH = {
         P.TASK_LAYER_FORWARD: "_t_layer_forward", P.TASK_LAYER_FORWARD_TRAIN: "_t_layer_forward_train",
@@ -268,6 +320,7 @@ class Coordinator:
         self.host, self.port, self.transport, self.name = host, port, transport, name
         self.workers: Dict[str, Dict[str, Any]] = {}
         self._pending: Dict[str, asyncio.Future] = {}
+        self.hop_log: List[Dict[str, Any]] = []        # per hop of the last hf pipeline: on-device or framed, frame size
         self._server = None
         self.addr = ""
 
@@ -376,7 +429,8 @@ class Coordinator:
             grad = np.asarray(res["dX"], dtype=np.float32)
         return loss
 
-    async def run_hf_pipeline(self, model_name: str, text: str, n_parts: Optional[int] = None) -> np.ndarray:
+    async def run_hf_pipeline(self, model_name: str, text: str, n_parts: Optional[int] = None,
+                              devices: Optional[List[str]] = None) -> np.ndarray:
         """RUN_HF_PIPELINE: split ``model_name`` into layer ranges over the workers, push ``text``
         through, return the last piece's output (logits of the final position)."""
         from .models.config import resolve_config, split_layers
@@ -386,19 +440,29 @@ class Coordinator:
         ranges = split_layers(cfg.n_layers, n_parts or len(ids))
         handles = []
         for i, r in enumerate(ranges):
-            res = await self.submit(ids[i % len(ids)], {"kind": P.HF_PART_LOAD, "model_name": model_name,
-                                                        "start": r.start, "end": r.stop if i < len(ranges) - 1 else cfg.n_layers})
-            handles.append((ids[i % len(ids)], res["model_id"]))
-        out = None
-        for i, (nid, mid) in enumerate(handles):
+            load = {"kind": P.HF_PART_LOAD, "model_name": model_name, "start": r.start,
+                    "end": r.stop if i < len(ranges) - 1 else cfg.n_layers}
+            if devices:
+                load["device"] = devices[i % len(devices)]
+            res = await self.submit(ids[i % len(ids)], load)
+            handles.append((ids[i % len(ids)], res["model_id"], res.get("backend") == "b200-native"))
+        out, ref = None, None
+        for i, (nid, mid, native) in enumerate(handles):
             payload = {"kind": P.HF_PART_FORWARD, "model_id": mid, "binary": True}
             if i == 0:
                 payload["text"] = text
+            elif ref is not None:
+                payload["hidden_ref"] = ref              # ~100-byte frame; the payload moves GPU -> GPU
             else:
                 payload["hidden_b64"] = out
-            out = (await self.submit(nid, payload))["hidden_b64"]
+            nxt_native = i + 1 < len(handles) and handles[i + 1][2]
+            payload["keep_on_device"] = bool(native and nxt_native)
+            res = await self.submit(nid, payload)
+            ref, out = res.get("hidden_ref"), res.get("hidden_b64")
+            self.hop_log.append({"stage": i, "on_device": ref is not None,
+                                 "frame_bytes": len(json.dumps(res))})
         from .parallel.cpu_pipeline import decode_tensor
 
-        for nid, mid in handles:
+        for nid, mid, _ in handles:
             await self.submit(nid, {"kind": P.HF_UNLOAD, "model_id": mid})
         return decode_tensor(out).float().numpy()[0, -1]

@@ -158,3 +158,45 @@ def test_graph_prefill_matches_eager_prefill():
         assert r.pf_chunks >= 5
         r.close()
     assert outs[0] == outs[1]
+
+
+def test_legacy_worker_hf_part_on_the_gpu_data_plane():
+    """C16 / VERDICT r1: hf_part_load / hf_part_forward run the layer range on NativePiece and the hop payload stays in
+    device memory (hidden_ref: cudaMemcpyPeerAsync of a cudaMalloc buffer, exportable as a CUDA IPC handle) instead of
+    the reference's JSON list of fp32 (/root/reference/bee2bee/node.py:270-277).  Result == whole-model oracle."""
+    import asyncio
+    import json
+
+    from bee2bee_b200 import protocol as P
+    from bee2bee_b200.engine.tokenizer import load_tokenizer
+    from bee2bee_b200.node import TaskExecutor
+
+    cfg = resolve_config("tiny-llama")
+    ex = TaskExecutor(device="cuda")
+    a = ex.execute({"kind": P.HF_PART_LOAD, "model_name": "tiny-llama", "start": 0, "end": 2})
+    b = ex.execute({"kind": P.HF_PART_LOAD, "model_name": "tiny-llama", "start": 2, "end": 4})
+    assert a["backend"] == b["backend"] == "b200-native"
+    text = "the mesh hops on the device"
+    r1 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": a["model_id"], "text": text, "keep_on_device": True})
+    ref = r1["hidden_ref"]
+    assert set(ref) == {"ref", "device", "shape", "ipc"} and len(json.dumps(r1)) < 400       # the frame is ~200 bytes
+    r2 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": b["model_id"], "hidden_ref": ref})
+    logits = torch.tensor(r2["hidden"])[0, -1]
+    # legacy framing through the same GPU pieces gives the same answer
+    l1 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": a["model_id"], "text": text, "session": "s2", "binary": True})
+    l2 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": b["model_id"], "hidden_b64": l1["hidden_b64"], "session": "s2"})
+    assert torch.allclose(torch.tensor(l2["hidden"])[0, -1], logits, atol=1e-3, rtol=1e-3)
+    # oracle: all four layers in fp32 on the same random-init weights
+    tok = load_tokenizer("tiny-llama", cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id)
+    ids = tok.encode(text)
+    t = init_random(cfg, range(cfg.n_layers), True, True, device="cuda", dtype=torch.float32)
+    oracle = TorchPiece(cfg, range(cfg.n_layers), True, True, t)
+    with torch.no_grad():
+        want = oracle.forward(torch.tensor([ids], device="cuda"), torch.arange(len(ids), device="cuda")[None])[0, -1]
+    assert _rel_err(logits.cuda(), want) < 0.2
+    cos = torch.nn.functional.cosine_similarity(logits.cuda().float(), want.float(), dim=0).item()
+    assert cos > 0.98, cos
+    # decode continues in the session's paged KV cache (no pos0: the piece tracks the session length)
+    r3 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": a["model_id"], "ids": [int(want.argmax())], "keep_on_device": True})
+    r4 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": b["model_id"], "hidden_ref": r3["hidden_ref"]})
+    assert len(r4["hidden"][0][0]) == cfg.vocab_size
