@@ -2,7 +2,7 @@
 has no multi-GPU path at all; this is the "path that only calls NCCL for the named ops" that
 BASELINE.json tells the product to beat, built by us with library calls only:
 
-  * the same piece split (half-layer units from ``models.config.piece_units`` rounded to whole layers) and the same
+  * the same piece split (``models.config.piece_units`` rounded to whole layers) and the same
     micro-batch groups / wavefront order as the product,
   * every op is a PyTorch library call: cuBLAS GEMMs (``torch.matmul``), ``F.scaled_dot_product_attention`` (flash /
     mem-efficient kernels) over a contiguous static KV cache, ATen RMSNorm / RoPE / SiLU, ATen sort + multinomial
@@ -55,8 +55,8 @@ class NcclPipeline:
         self.groups, self.gb, self.max_len = groups, group_batch, max_len
         self.first, self.last = rank == 0, rank == world - 1
         units = piece_units(c, world)
-        # whole layers: a half-layer cut would need a second payload (residual + attention output) per hop
-        cuts = [0] + [min(c.n_layers, (u1 + 1) // 2) for _, u1 in units]
+        # whole layers (nearest boundary): a cut inside a layer would need extra payloads per hop
+        cuts = [0] + [min(c.n_layers, (u1 + 1) // 3) for _, u1 in units]
         cuts[-1] = c.n_layers
         for i in range(1, len(cuts)):
             cuts[i] = max(cuts[i], cuts[i - 1] + 1) if i < len(cuts) - 1 else cuts[i]

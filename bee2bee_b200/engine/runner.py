@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..models.config import ModelConfig, piece_units
+from ..models.config import UNITS_PER_LAYER, ModelConfig, piece_units, unit_layers
 from ..models.native import BatchMeta, NativePiece
 from ..models.weights import load_or_init
 from ..parallel.mesh import F_TOK_DONE, M_PF_SEEN, MeshComm
@@ -86,14 +86,17 @@ class GpuRunner:
         # token history ring per slot: the scheduler reads every burst's window before the sampler can lap it
         self.hist_len = hist_len if hist_len > 0 else max(256, min(4096, _pow2_at_least(max_seq_len)))
         self.use_graphs = use_graphs
-        # piece boundaries in half-layer units (attention block | MLP block), balanced for the wavefront: the last
-        # piece also streams the lm_head and runs the sampler.  B2B_UNIT_BOUNDS="0,3,8" overrides the search (tests).
+        # piece boundaries in third-of-a-layer units (attention block | gate/up GEMM | down GEMM), balanced for the
+        # wavefront: the last piece also streams the lm_head and runs the sampler.  B2B_UNIT_BOUNDS="0,4,12" overrides the
+        # search (tests).
         env_bounds = os.environ.get("B2B_UNIT_BOUNDS", "")
         bounds = [int(v) for v in env_bounds.split(",")] if env_bounds and world > 1 else None
         self.unit_ranges = piece_units(cfg, world, bounds)
         assert len(self.unit_ranges) == world, f"{cfg.name}: cannot split into {world} pieces ({self.unit_ranges})"
         self.units = self.unit_ranges[rank]
-        self.layers = list(range(self.units[0] // 2, (self.units[1] + 1) // 2))
+        self.layers = list(unit_layers(self.units))
+        # a cut between a gate/up and a down GEMM anywhere in the mesh -> every hop slot also stages the MLP hidden
+        mlp_cut = any(u1 % UNITS_PER_LAYER == 2 for _, u1 in self.unit_ranges[:-1])
         self.first, self.last = rank == 0, rank == world - 1
         if num_pages <= 0:
             num_pages = 1 + max_batch * self.max_pages_per_seq
@@ -107,7 +110,7 @@ class GpuRunner:
                                  self.max_chunk_seqs, num_pages, quant=quant, units=self.units)
         del tensors
         self.mesh = MeshComm(rank, world, self.device, cfg.hidden_size, max_tokens, groups, self.gb, self.hist_len,
-                             control_group)
+                             control_group, ffn=cfg.ffn_size if mlp_cut else 0)
         self.C = ops.native()
         dev, i32 = self.device, torch.int32
         B = max_batch
@@ -171,7 +174,8 @@ class GpuRunner:
         if self.piece.fp8:
             per += 4                             # activation quantisers (QKV, O, gate/up, down inputs)
         total = 1 + n * per                      # decode_advance + layers
-        total -= (3 if self.piece.head_skip_attn else 0) + (2 if self.piece.tail_skip_mlp else 0)   # half-layer ends
+        if per == 5 and not self.piece.fp8:
+            total = 1 + self.piece.n_launches()  # sub-layer piece ends: count the GEMMs / attention actually present
         if self.first:
             total += 1                           # embed
         if self.last:
@@ -285,16 +289,18 @@ class GpuRunner:
         st = {"stage": stage, "v": v, "hosts": hosts, "hosts_np": [t.numpy() for t in hosts], "events": [None] * 4,
               "turn": 0, "graph": None, "n": n}
         hand = self.mesh.handoff_prefill(parity) if self.world > 1 else None
-        x_in = None
+        x_in = h_in = None
         if not self.first:
             x_in = self.C.tensor_from_ptr(hand.in_x, [tb, self.cfg.hidden_size], "bf16", dev.index)
+            if self.piece.head_mode == 2:
+                h_in = self.C.tensor_from_ptr(hand.in_h, [tb, self.cfg.ffn_size], "bf16", dev.index)
         meta = BatchMeta(ids=v["ids"], positions=v["pos"], slots=v["slots"], q_start=v["q_start"], q_len=v["q_len"],
                          kv_len=v["kv_len"], block_table=v["bt"], n_tokens=tb, n_seqs=sb, max_q=mq,
                          last_idx=v["last_idx"])
         st["meta"] = meta       # captured kernels address these views by raw pointer: keep them alive
 
         def body():
-            out = self.piece.forward(meta, x_in=x_in, hand=hand)
+            out = self.piece.forward(meta, x_in=x_in, hand=hand, h_in=h_in)
             if self.last:
                 multi = self.world > 1
                 ops.sample(out, self.tok_local if multi else self.tokens, seen=self.seen, temperature=self.temperature,
@@ -378,10 +384,12 @@ class GpuRunner:
         meta = BatchMeta(ids=self._grp(self.tokens, g), positions=pos, slots=slots, q_start=self.q_start, q_len=ql,
                          kv_len=kvl, block_table=bt, n_tokens=gb, n_seqs=gb, max_q=1, splits=self.decode_splits)
         hand = self.mesh.handoff(g)
-        x_in = None
+        x_in = h_in = None
         if not self.first:
             x_in = self.C.tensor_from_ptr(hand.in_x, [gb, self.cfg.hidden_size], "bf16", self.device.index)
-        out = self.piece.forward(meta, x_in=x_in, hand=hand if self.world > 1 else None)
+            if self.piece.head_mode == 2:
+                h_in = self.C.tensor_from_ptr(hand.in_h, [gb, self.cfg.ffn_size], "bf16", self.device.index)
+        out = self.piece.forward(meta, x_in=x_in, hand=hand if self.world > 1 else None, h_in=h_in)
         if self.last:
             multi = self.world > 1
             hist_ptr = (self.mesh.history_ptr(g) if multi else self._grp(self.history, g).data_ptr())

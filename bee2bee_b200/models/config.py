@@ -262,30 +262,36 @@ def supports_half_layer_pieces(cfg: "ModelConfig") -> bool:
     return cfg.norm == "rms" and not cfg.post_norms and cfg.glu and not cfg.bias
 
 
+UNITS_PER_LAYER = 3       # attention block (QKV GEMM, attention, O-proj) | gate/up GEMM | down GEMM
+
+
 def piece_units(cfg: "ModelConfig", pieces: int, bounds: Optional[List[int]] = None) -> List[tuple]:
-    """Piece boundaries in HALF-LAYER units: unit 2l is the attention block of layer l (QKV GEMM, attention,
-    O-proj), unit 2l+1 its MLP block (gate/up, down).  Returns ``pieces`` contiguous ``(u0, u1)`` ranges that
-    minimise the heaviest stage of the wavefront under a bytes-plus-launch-latency cost model (a decode step is
-    weight-bandwidth bound with ~10 us of fixed cost per kernel); the last piece also carries the lm_head and
-    the sampler.  Llama-3-8B over 8 GPUs: whole layers give 5/4/4/4/4/4/4/3 (+head) = 0.81 scaling, half layers
-    bring every stage within one MLP block of the mean.  ``bounds`` overrides the search (tests)."""
-    U = 2 * cfg.n_layers
+    """Piece boundaries in THIRD-OF-A-LAYER units: unit 3l is the attention block of layer l (QKV GEMM, attention,
+    O-proj), 3l+1 its gate/up GEMM, 3l+2 its down GEMM -- any GEMM can be the fused tail GEMM of a piece and any GEMM
+    its head.  Returns ``pieces`` contiguous ``(u0, u1)`` ranges that minimise the heaviest stage of the wavefront under
+    a bytes-plus-launch-latency cost model (a decode step is weight-bandwidth bound with a few us of fixed cost per
+    kernel); the last piece also carries the lm_head and the sampler.  Llama-3-8B over 8 GPUs: whole layers give
+    5/4/4/4/4/4/4/3 (+head) = 0.81 of the ideal stage time, half layers (round 1) 0.92, thirds 0.97.  ``bounds``
+    overrides the search (tests).  Graphs without the fused RMSNorm / GLU epilogues are cut at whole layers."""
+    UPL = UNITS_PER_LAYER
+    U = UPL * cfg.n_layers
     if bounds is not None:
         assert bounds[0] == 0 and bounds[-1] == U and all(a < b for a, b in zip(bounds, bounds[1:])), bounds
         return list(zip(bounds[:-1], bounds[1:]))
     pieces = max(1, min(pieces, cfg.n_layers))
     if pieces == 1 or not supports_half_layer_pieces(cfg):
-        return [(2 * r.start, 2 * r.stop) for r in balanced_split(cfg, pieces)]
+        return [(UPL * r.start, UPL * r.stop) for r in balanced_split(cfg, pieces)]
     # stage time model fitted to the measured decode step (profiles/decode_layer_breakdown.md, B200, 32 sequences):
-    # weight bytes at the measured 6.4 TB/s plus ~7 us per kernel launch; the last piece adds the lm_head GEMM and the
-    # 30 us sampler.  Llama-3-8B: attention block 34 us (measured 36.6), MLP block 69 (65), head 201 (213).
+    # weight bytes at the measured 6.4 TB/s plus a fixed cost per kernel; the last piece adds the lm_head GEMM and the
+    # sampler.  Llama-3-8B: attention block 34.1 us (measured 34.7), gate/up 40.7 (39.4), down 25.3 (24.9), head 201 (211).
     h, f = cfg.hidden_size, cfg.ffn_size
     us_per_elem = 2.0 / 6.4e6                            # bf16 element -> microseconds of HBM streaming
     launch = 7.0
     attn = (h * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.q_dim * h) * us_per_elem + 3 * launch
-    mlp = 3 * h * f * us_per_elem + 2 * launch
+    gu = 2 * h * f * us_per_elem + 4.0
+    down = h * f * us_per_elem + launch
     head = cfg.vocab_size * h * us_per_elem + launch + 30.0
-    cost = [attn if u % 2 == 0 else mlp for u in range(U)]
+    cost = [(attn, gu, down)[u % UPL] for u in range(U)]
     pre = [0.0]
     for c in cost:
         pre.append(pre[-1] + c)
@@ -296,7 +302,7 @@ def piece_units(cfg: "ModelConfig", pieces: int, bounds: Optional[List[int]] = N
     best[0][0] = 0.0
     for k in range(1, pieces + 1):
         for u in range(k, U + 1):
-            for v in range(k - 1, u - 1):          # every piece spans >= 2 units (no lone attention / MLP block)
+            for v in range(k - 1, u - 1):          # every piece spans >= 2 units (no lone GEMM)
                 if best[k - 1][v] == INF:
                     continue
                 stage = pre[u] - pre[v] + (head if (k == pieces and u == U) else 0.0)
@@ -309,3 +315,8 @@ def piece_units(cfg: "ModelConfig", pieces: int, bounds: Optional[List[int]] = N
         out.append((v, u))
         u = v
     return out[::-1]
+
+
+def unit_layers(units: tuple) -> range:
+    """layers touched by a ``(u0, u1)`` unit range"""
+    return range(units[0] // UNITS_PER_LAYER, (units[1] - 1) // UNITS_PER_LAYER + 1)

@@ -37,6 +37,8 @@ class Handoff:
     "input" is the sampled-token buffer written by the last piece; for the last piece the
     "output" is that token buffer on piece 0."""
     in_x: int = 0            # [max_tokens, H] bf16 staging buffer (local); piece 0: int32 token buffer
+    in_h: int = 0            # [max_tokens, F] bf16 staging of the MLP hidden (local): piece starts at a down GEMM
+    out_h: int = 0           # downstream in_h (peer): piece ends with a gate/up GEMM
     in_flag: int = 0         # u32: upstream publishes its epoch here (local)
     in_epoch: int = 0        # u32: number of inputs already consumed (local)
     up_ack: int = 0          # u32 on the upstream rank: its out_free for our input slot
@@ -69,19 +71,24 @@ class NativePiece:
     def __init__(self, cfg: ModelConfig, layers: Iterable[int], first: bool, last: bool, tensors: Tensors,
                  device: torch.device, max_tokens: int, max_seqs: int, num_pages: int, quant: str = "bf16",
                  units: Optional[tuple] = None):
-        # ``units`` = (u0, u1) in half-layer units (2l = attention block of layer l, 2l+1 = its MLP block); a piece
-        # may start at an MLP block (the upstream piece ran that layer's attention) and / or end after an
-        # attention block (config.piece_units).  Default: whole layers.
+        # ``units`` = (u0, u1) in THIRD-of-a-layer units: 3l = attention block of layer l (QKV GEMM, attention, O-proj),
+        # 3l+1 = its gate/up GEMM, 3l+2 = its down GEMM (config.piece_units).  A piece may start at any of them (the
+        # upstream piece ran the earlier ops of that layer) and end after any of them -- every GEMM can be the fused
+        # tail GEMM that stores into the peer, every GEMM can be the head GEMM that acquires the flag.  A cut between
+        # gate/up and down hands off TWO payloads: the MLP hidden [T, F] and the residual stream [T, H] (which the
+        # O-proj epilogue of that layer dual-stores to the peer).  Default: whole layers.
         if units is not None:
-            layers = range(units[0] // 2, (units[1] + 1) // 2)
-            self.head_skip_attn, self.tail_skip_mlp = units[0] % 2 == 1, units[1] % 2 == 1
+            layers = range(units[0] // 3, (units[1] - 1) // 3 + 1)
+            self.head_mode, self.tail_mode = units[0] % 3, (units[1] - 1) % 3
         else:
-            self.head_skip_attn = self.tail_skip_mlp = False
+            self.head_mode, self.tail_mode = 0, 2
         self.cfg, self.layers, self.first, self.last = cfg, list(layers), first, last
-        if self.head_skip_attn or self.tail_skip_mlp:
+        self.head_skip_attn, self.tail_skip_mlp = self.head_mode > 0, self.tail_mode < 2       # (reporting)
+        if self.head_mode != 0 or self.tail_mode != 2:
             from .config import supports_half_layer_pieces
-            assert supports_half_layer_pieces(cfg), "half-layer piece boundaries need the fused RMSNorm / GLU graph"
-            assert not (self.tail_skip_mlp and last), "the last piece ends with a whole layer"
+            assert supports_half_layer_pieces(cfg), "sub-layer piece boundaries need the fused RMSNorm / GLU graph"
+            assert not (self.tail_mode != 2 and last), "the last piece ends with a whole layer"
+            assert not (self.head_mode != 0 and first), "the first piece starts with a whole layer"
         self.device = torch.device(device)
         self.max_tokens, self.max_seqs, self.num_pages = max_tokens, max_seqs, num_pages
         self.fused_norm = cfg.norm == "rms"
@@ -100,7 +107,7 @@ class NativePiece:
         for l in self.layers:
             p = f"l{l}."
             if not self.has_attn(l):
-                self._load_mlp_only(t, p)
+                self._load_mlp_only(t, p, l)
                 continue
             wq, wk, wv = t[p + "wq"], t[p + "wk"], t[p + "wv"]
             if c.rope_theta > 0:
@@ -111,7 +118,7 @@ class NativePiece:
                 wqkv = ops.fold_gamma(wqkv, t[p + "ln1_w"], c.gemma_norm)
             self.w[p + "wqkv"] = wqkv.contiguous()
             self.w[p + "wo"] = t[p + "wo"].contiguous()
-            if not self.has_mlp(l):
+            if not self.has_gu(l):
                 continue
             if c.glu:
                 wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
@@ -120,7 +127,8 @@ class NativePiece:
                 self.w[p + "wgu"] = wgu
             else:
                 self.w[p + "w_up"] = t[p + "w_up"].contiguous()
-            self.w[p + "w_down"] = t[p + "w_down"].contiguous()
+            if self.has_down(l):
+                self.w[p + "w_down"] = t[p + "w_down"].contiguous()
             if not self.fused_norm:
                 for n in ("ln1_w", "ln1_b", "ln2_w", "ln2_b"):
                     self.w[p + n] = t[p + n]
@@ -185,17 +193,32 @@ class NativePiece:
 
     # ------------------------------------------------------------------ helpers
     def has_attn(self, l: int) -> bool:
-        return not (self.head_skip_attn and l == self.layers[0])
+        return not (self.head_mode > 0 and l == self.layers[0])
+
+    def has_gu(self, l: int) -> bool:
+        return not (self.head_mode == 2 and l == self.layers[0]) and not (self.tail_mode == 0 and l == self.layers[-1])
+
+    def has_down(self, l: int) -> bool:
+        return not (self.tail_mode < 2 and l == self.layers[-1])
 
     def has_mlp(self, l: int) -> bool:
-        return not (self.tail_skip_mlp and l == self.layers[-1])
+        return self.has_gu(l) and self.has_down(l)
 
-    def _load_mlp_only(self, t, p: str) -> None:
-        """first layer of a piece that starts at the MLP block (fused-norm GLU graphs only)"""
+    def n_launches(self) -> int:
+        """kernel launches of one forward through the layers of this piece (fused-norm graphs; reporting)"""
+        n = 0
+        for l in self.layers:
+            n += (3 if self.has_attn(l) else 0) + (1 if self.has_gu(l) else 0) + (1 if self.has_down(l) else 0)
+        return n
+
+    def _load_mlp_only(self, t, p: str, l: int) -> None:
+        """first layer of a piece that starts inside the layer (fused-norm GLU graphs only)"""
         c = self.cfg
-        wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
-        self.w[p + "wgu"] = ops.fold_gamma(wgu, t[p + "ln2_w"], c.gemma_norm)
-        self.w[p + "w_down"] = t[p + "w_down"].contiguous()
+        if self.has_gu(l):
+            wgu = ops.glu_interleave_rows(t[p + "w_gate"], t[p + "w_up"])
+            self.w[p + "wgu"] = ops.fold_gamma(wgu, t[p + "ln2_w"], c.gemma_norm)
+        if self.has_down(l):
+            self.w[p + "w_down"] = t[p + "w_down"].contiguous()
 
     def _quant(self, x: torch.Tensor, with_rms: bool):
         """bf16 rows -> (e4m3 rows, activation-side gemm kwargs) in the preallocated staging buffers.
@@ -227,7 +250,7 @@ class NativePiece:
 
     # ------------------------------------------------------------------ forward
     def forward(self, m: BatchMeta, x_in: Optional[torch.Tensor] = None, hand: Optional[Handoff] = None,
-                out_x: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out_x: Optional[torch.Tensor] = None, h_in: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Runs the piece for the tokens described by ``m``.
 
         first piece: embeds ``m.ids``; otherwise reads ``x_in`` ([T, H], may be the peer-written
@@ -250,7 +273,8 @@ class NativePiece:
         n_layers = len(self.layers)
         for li, l in enumerate(self.layers):
             p = f"l{l}."
-            do_attn, do_mlp = self.has_attn(l), self.has_mlp(l)
+            do_attn, do_gu, do_down = self.has_attn(l), self.has_gu(l), self.has_down(l)
+            do_mlp = do_gu          # the piece continues past this layer's attention block
             is_tail = (li == n_layers - 1) and not self.last
             head_wait = wait_flag if li == 0 else 0           # the piece's first GEMM consumes the handoff input
             head_epoch = wait_epoch if li == 0 else 0
@@ -298,6 +322,13 @@ class NativePiece:
                 a = self.attn_buf[:T]
                 okw = {} if do_mlp else tail_kw          # piece ends after this attention block: O-proj is the tail GEMM
                 o_out = None if okw else x2
+                if is_tail and do_gu and not do_down and hand.out_x:
+                    # the piece ends with this layer's gate/up GEMM: the next piece's down GEMM needs the residual stream
+                    # too -> the O-proj epilogue stores x2 locally AND into the peer's staging slot (flow-controlled like
+                    # the tail GEMM's own payload; the tail GEMM's release flag publishes both)
+                    okw = dict(out2_ptr=hand.out_x, free_flag=hand.out_free, signal_epoch=hand.out_epoch,
+                               free_lag=hand.free_lag)
+                    o_out = x2
                 if c.post_norms:
                     o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
                     ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
@@ -312,24 +343,34 @@ class NativePiece:
                     x = out_x[:T] if (okw and out_x is not None and not hand.out_x) else x2
                     continue
             # ---------------- MLP block
-            mlp_wait = head_wait if not do_attn else 0      # piece starts at this MLP block: gate/up consumes the input
+            mlp_wait = head_wait if not do_attn else 0      # piece starts inside this layer: its first GEMM consumes the input
             mlp_epoch = head_epoch if not do_attn else 0
             if mlp_wait and (self.fp8 or not inline):
-                ops.native().flag_wait(mlp_wait, mlp_epoch, 1)   # a separate quant / 1/rms kernel reads x2 first
-            if c.glu and self.fp8:
+                ops.native().flag_wait(mlp_wait, mlp_epoch, 1)   # a separate quant / 1/rms kernel reads the input first
+            gu_tail = tail_kw if (do_gu and not do_down) else {}   # piece ends after gate/up: it is the tail GEMM
+            if gu_tail and hand.out_h:
+                gu_tail = dict(gu_tail, out_ptr=hand.out_h, ld_out=c.ffn_size)
+            if not do_gu:
+                hmid = h_in[:T]                              # the upstream piece ran gate/up: staged MLP hidden
+            elif c.glu and self.fp8:
                 x2q, akw = self._quant(x2, with_rms=True)
-                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=self.h_buf[:T], epi=ops.EPI_GLU, **akw,
-                                **self._wkw(p + "wgu"), act_gelu=(c.act == "gelu_tanh"))
+                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=None if gu_tail else self.h_buf[:T], epi=ops.EPI_GLU, **akw,
+                                **self._wkw(p + "wgu"), act_gelu=(c.act == "gelu_tanh"), **gu_tail)
             elif c.glu:
                 r2 = None
                 if self.fused_norm and not inline:
                     r2 = ops.rstd(x2, eps)
-                hmid = ops.gemm(self.w[p + "wgu"], x2, out=self.h_buf[:T], epi=ops.EPI_GLU, rstd=r2,
+                hmid = ops.gemm(self.w[p + "wgu"], x2, out=None if gu_tail else self.h_buf[:T], epi=ops.EPI_GLU, rstd=r2,
                                 norm_from_x=inline and self.fused_norm, eps=eps, act_gelu=(c.act == "gelu_tanh"),
-                                wait_flag=mlp_wait, wait_epoch=mlp_epoch)
+                                wait_flag=mlp_wait, wait_epoch=mlp_epoch, **gu_tail)
             else:
                 n2 = ops.layernorm(x2, self.w[p + "ln2_w"], self.w[p + "ln2_b"], self.n_buf[:T], eps)
                 hmid = ops.gemm(self.w[p + "w_up"], n2, out=self.h_buf[:T], epi=ops.EPI_GELU, bias=self.w.get(p + "b_up"))
+            if not do_down:
+                x = x2                   # (not read again: the piece ends here)
+                continue
+            down_wait = mlp_wait if not do_gu else 0         # piece starts at this down GEMM
+            down_epoch = mlp_epoch if not do_gu else 0
             if c.post_norms:
                 d = ops.gemm(self.w[p + "w_down"], hmid, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
                 if is_tail and hand.out_x:
@@ -352,7 +393,8 @@ class NativePiece:
                              residual=x2, **akw, **self._wkw(p + "w_down"), **tail_kw)
                 else:
                     ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
-                             residual=x2, bias=self.w.get(p + "b_down"), **tail_kw)
+                             residual=x2, bias=self.w.get(p + "b_down"), wait_flag=down_wait, wait_epoch=down_epoch,
+                             **tail_kw)
                 if tail_kw and out_x is not None and not hand.out_x:
                     xn = out_x[:T]
             x = xn

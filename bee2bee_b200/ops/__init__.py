@@ -159,7 +159,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
          dbg: int = 0, w_scale: Optional[torch.Tensor] = None,
          sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1, pf: int = -1,
-         stages: int = -1, free_lag: int = 0) -> Optional[torch.Tensor]:
+         stages: int = -1, free_lag: int = 0, out2_ptr: int = 0) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -198,7 +198,7 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
                   ack_flag, dbg, w_scale, sfa, sfb, GEMM_MC if mc < 0 else mc,
-                  L2_PREFETCH if pf < 0 else pf, stages, free_lag)
+                  L2_PREFETCH if pf < 0 else pf, stages, free_lag, out2_ptr)
     return out
 
 

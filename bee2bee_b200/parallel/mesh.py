@@ -42,10 +42,12 @@ class MeshComm:
     """Per-rank view of the pipeline ring rank0 -> rank1 -> ... -> rank(W-1) -> rank0 (tokens)."""
 
     def __init__(self, rank: int, world: int, device: torch.device, hidden: int, max_tokens: int, groups: int,
-                 group_batch: int, hist_len: int, control_group=None):
+                 group_batch: int, hist_len: int, control_group=None, ffn: int = 0):
+        # ffn > 0: some piece boundary lies between a gate/up and a down GEMM -> the hop also carries the MLP hidden
         self.rank, self.world, self.device = rank, world, torch.device(device)
         self.hidden, self.max_tokens, self.groups, self.group_batch, self.hist_len = hidden, max_tokens, groups, group_batch, hist_len
         self.control_group = control_group
+        self.ffn = ffn
         self.next_rank = (rank + 1) % world
         self.prev_rank = (rank - 1) % world
         self.peers: Dict[int, PeerInfo] = {}
@@ -63,6 +65,8 @@ class MeshComm:
         return {
             "stage": self.groups * self.group_batch * self.hidden * 2,          # decode: one bf16 slot per group
             "stage_pf": 2 * self.max_tokens * self.hidden * 2,                  # prefill chunks: double-buffered
+            "stage_h": self.groups * self.group_batch * self.ffn * 2,           # MLP hidden of a gate/up | down cut
+            "stage_h_pf": 2 * self.max_tokens * self.ffn * 2,
             "flags": (self.groups + 2) * FLAG_WORDS * 4,                        # groups, prefill channel, misc
             "tok": self.groups * self.group_batch * 4,                          # sampled-token return buffer (rank 0)
             "hist": self.groups * self.group_batch * self.hist_len * 4,         # token history ring (rank 0)
@@ -127,12 +131,17 @@ class MeshComm:
         h.out_epoch = self._flag(self.local, group, F_OUT_EPOCH)
         h.done = self._flag(self.local, group, F_DONE)
         h.in_x = (self.local["tok"] + tok_off) if first else (self.local["stage"] + stage_off)
+        h_off = group * self.group_batch * self.ffn * 2
+        if self.ffn and not first:
+            h.in_h = self.local["stage_h"] + h_off
         if last:
             h.out_x = self.remote_first["tok"] + tok_off
             h.out_flag = self._flag(self.remote_first, group, F_IN_FLAG)
         else:
             h.out_x = self.remote_next["stage"] + stage_off
             h.out_flag = self._flag(self.remote_next, group, F_IN_FLAG)
+            if self.ffn:
+                h.out_h = self.remote_next["stage_h"] + h_off
         return h
 
     def handoff_prefill(self, parity: int) -> Handoff:
@@ -148,12 +157,17 @@ class MeshComm:
         h = Handoff()
         h.done = self._flag(self.local, c, F_DONE)
         h.free_lag = 1
+        h_off = parity * self.max_tokens * self.ffn * 2
         if not first:
             h.in_x = self.local["stage_pf"] + off
+            if self.ffn:
+                h.in_h = self.local["stage_h_pf"] + h_off
             h.in_flag = self._flag(self.local, c, F_IN_FLAG)
             h.in_epoch = self._flag(self.local, c, F_IN_EPOCH)
             h.up_ack = self._flag(self.remote_prev, c, F_OUT_FREE)
         if not last:
+            if self.ffn:
+                h.out_h = self.remote_next["stage_h_pf"] + h_off
             h.out_x = self.remote_next["stage_pf"] + off
             h.out_flag = self._flag(self.remote_next, c, F_IN_FLAG)
             h.out_epoch = self._flag(self.local, c, F_OUT_EPOCH)

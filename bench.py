@@ -269,7 +269,7 @@ def run_ours(args):
                "data": "synthetic", "impl": "ours",
                "config": common_fields(args, world, total, K, W, P, {
                    "parallelism": f"pp{world}",
-                   "piece_units": "/".join(str(b - a) for a, b in eng.runner.unit_ranges) + " half-layers",
+                   "piece_units": "/".join(str(b - a) for a, b in eng.runner.unit_ranges) + " thirds of a layer (attention block | gate/up | down)",
                    "micro_batch_groups": groups, "batch_per_group": B}),
                "p50_ttft_ms": statistics.median(ttfts), "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
                "roofline": {"accounting": "bytes a decode step streams per rank (weights without the gathered embedding "

@@ -46,7 +46,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
           int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale,
-          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages, int64_t free_lag) {
+          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages, int64_t free_lag, int64_t out2_ptr) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
@@ -87,6 +87,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.sfb = fp8 ? ptr_or_null<const uint8_t>(sfb) : nullptr;
   p.out = as_ptr<void>(out_ptr);
   p.ld_out = static_cast<int>(ld_out);
+  p.out2 = as_ptr<void>(out2_ptr);
   p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
   p.ld_res = static_cast<int>(ld_res);
   p.bias = ptr_or_null<const float>(bias);

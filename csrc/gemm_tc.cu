@@ -485,8 +485,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
               __float2bfloat16_rn(gelu_tanh(a));
         } else if constexpr (EPI == EPI_RESIDUAL) {
-          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
-              __float2bfloat16_rn(a + __bfloat162float(resid[i]));
+          const __nv_bfloat16 r16 = __float2bfloat16_rn(a + __bfloat162float(resid[i]));
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
+          if (p.out2 != nullptr)
+            reinterpret_cast<__nv_bfloat16*>(p.out2)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
         } else if constexpr (EPI == EPI_GLU) {
           const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);

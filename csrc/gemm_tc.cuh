@@ -38,6 +38,7 @@ struct GemmParams {
 
   void* out;          // [m_tok, ld_out]
   int ld_out;
+  void* out2;         // EPI_RESIDUAL: optional second destination with the same layout (e.g. the peer's staging slot), or null
   const __nv_bfloat16* residual;  // [m_tok, ld_res]
   int ld_res;
   const float* bias;              // [n_out] or null

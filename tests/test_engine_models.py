@@ -249,22 +249,23 @@ def test_piece_units_cover_the_model_and_balance_the_wavefront():
     assert supports_half_layer_pieces(cfg)
     for n in (1, 2, 4, 8):
         units = piece_units(cfg, n)
-        assert len(units) == n and units[0][0] == 0 and units[-1][1] == 2 * cfg.n_layers
+        assert len(units) == n and units[0][0] == 0 and units[-1][1] == 3 * cfg.n_layers
         assert all(a[1] == b[0] for a, b in zip(units, units[1:])) and all(u1 > u0 for u0, u1 in units)
     # the last piece also streams the 1 GB lm_head: it gets the fewest units, nobody gets more than the mean + one layer
     u8 = piece_units(cfg, 8)
     sizes = [b - a for a, b in u8]
-    assert sizes[-1] == min(sizes) and max(sizes) <= 9 and any(a % 2 or b % 2 for a, b in u8)   # half-layer cuts are used
+    assert sizes[-1] == min(sizes) and max(sizes) <= 13 and any(b % 3 for a, b in u8)   # cuts inside layers are used
+    assert any(b % 3 == 2 for a, b in u8[:-1])           # ... including one between a gate/up and a down GEMM
     # whole-layer fallback for graphs whose boundary GEMMs are not the fused kinds (post-norms / LayerNorm)
     for name in ("gemma-2-2b", "distilgpt2"):
         c = resolve_config(name)
         assert not supports_half_layer_pieces(c)
-        assert piece_units(c, 2) == [(2 * r.start, 2 * r.stop) for r in balanced_split(c, 2)]
+        assert piece_units(c, 2) == [(3 * r.start, 3 * r.stop) for r in balanced_split(c, 2)]
     # explicit bounds (tests / experiments)
     tiny = resolve_config("tiny-llama")
-    assert piece_units(tiny, 2, [0, 3, 8]) == [(0, 3), (3, 8)]
+    assert piece_units(tiny, 2, [0, 5, 12]) == [(0, 5), (5, 12)]
     with pytest.raises(AssertionError):
-        piece_units(tiny, 2, [0, 9])
+        piece_units(tiny, 2, [0, 13])
 
 
 def test_mx_block_scaled_quantisation_roundtrip_cpu():

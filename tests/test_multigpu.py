@@ -37,21 +37,23 @@ def test_two_gpu_pipeline_matches_single_gpu(model):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("bounds", ["0,3,8", "0,5,8"])
-def test_two_gpu_half_layer_piece_boundary(bounds):
-    """Piece boundary inside a layer: piece 0 ends with an attention block (O-proj is the fused tail GEMM that
-    stores into the peer), piece 1 starts at the MLP block (gate/up is the head GEMM that acquires the flag)."""
+@pytest.mark.parametrize("bounds", ["0,4,12", "0,7,12", "0,5,12", "0,8,12", "0,2,12"])
+def test_two_gpu_sub_layer_piece_boundary(bounds):
+    """Piece boundary inside a layer (units = attention block | gate/up | down, 3 per layer).  After an attention block
+    (4, 7): O-proj is the fused tail GEMM that stores into the peer, gate/up the head GEMM that acquires the flag.
+    After a gate/up GEMM (5, 8, 2): gate/up is the tail GEMM (MLP hidden -> peer), the O-proj epilogue of that layer
+    dual-stores the residual stream to the peer, and the peer's head GEMM is the down projection."""
     ref = _run(1, "tiny-llama", 2, 4, 0)
     got = _run(2, "tiny-llama", 2, 4, 29617, B2B_UNIT_BOUNDS=bounds)
     assert got == ref
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("bounds", ["0,1,8", "0,7,8", "0,4,8"])
+@pytest.mark.parametrize("bounds", ["0,1,12", "0,10,12", "0,6,12", "0,5,12"])
 @pytest.mark.parametrize("prompts", ["bigsmall", "long"])
 def test_two_gpu_multichunk_prefill_backpressure(bounds, prompts):
     """VERDICT r1 #9 / ADVICE high: >= 16 prefill chunks of very different cost through deliberately unbalanced
-    pieces (a 1-unit producer in front of a 7-unit consumer and the reverse).  Without the device-side
+    pieces (a 1-unit producer in front of an 11-unit consumer, the reverse, and a cut inside an MLP block).  Without the device-side
     back-pressure (release / ack flags, double-buffered staging) the fast producer overwrites the staging slot
     while the consumer still reads the previous chunk (QKV input + O-proj residual) and the KV / first tokens
     are silently corrupted; with it the tokens equal the single-GPU run bit for bit."""
@@ -69,6 +71,17 @@ def test_two_gpu_engine_waves_match_single_gpu():
     ref = _run(1, "tiny-llama", 2, 4, 0, **kw)
     got = _run(2, "tiny-llama", 2, 4, 29621, **kw)
     assert got == ref
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("quant", ["mxfp8", "fp8"])
+def test_two_gpu_fp8_pipeline_matches_single_gpu(quant):
+    """BASELINE config 3 shape: block-scaled (mxfp8) / per-row fp8 pieces across the NVLink handoff, incl. a cut
+    between a gate/up and a down GEMM, equal the single-GPU fp8 engine token for token."""
+    kw = dict(B2B_QUANT=quant, B2B_STEPS="6")
+    ref = _run(1, "tiny-llama", 2, 4, 0, **kw)
+    assert _run(2, "tiny-llama", 2, 4, 29625, **kw) == ref
+    assert _run(2, "tiny-llama", 2, 4, 29627, B2B_UNIT_BOUNDS="0,5,12", **kw) == ref
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 8, reason="needs 8 GPUs")

@@ -18,6 +18,7 @@ groups = int(os.environ.get("B2B_GROUPS", "0"))
 B = int(os.environ.get("B2B_BATCH", "4"))
 pf_tokens = int(os.environ.get("B2B_PF_TOKENS", "128"))
 kind = os.environ.get("B2B_PROMPTS", "ramp")
+quant = os.environ.get("B2B_QUANT", "bf16")
 rank, world, local = init_distributed()
 cfg = resolve_config(model)
 groups = groups or world
@@ -41,7 +42,7 @@ prompts = [[(13 * i + 7 * j + 5) % (V - 8) + 4 for j in range(plen(i))] for i in
 if os.environ.get("B2B_ENGINE") == "1":
     from bee2bee_b200.engine.core import Engine, SamplingParams
     eng = Engine(model, cfg=cfg, device=f"cuda:{local}", max_batch=total, groups=groups, max_seq_len=max_seq,
-                 max_prefill_tokens=pf_tokens, decode_burst=max(1, steps // 3), rank=rank, world=world)
+                 max_prefill_tokens=pf_tokens, decode_burst=max(1, steps // 3), rank=rank, world=world, quant=quant)
     half = total // 2
     sp = SamplingParams(max_new_tokens=steps + 1, temperature=0.0, top_p=1.0, repetition_penalty=1.0, ignore_eos=True)
     # two waves: the second prefill lands between decode bursts of the first (flags are never reset)
@@ -56,7 +57,7 @@ if os.environ.get("B2B_ENGINE") == "1":
     eng.close()
 else:
     r = GpuRunner(cfg, "", rank, world, torch.device(f"cuda:{local}"), max_batch=total, groups=groups, max_seq_len=max_seq,
-                  max_prefill_tokens=pf_tokens, seed=0)
+                  max_prefill_tokens=pf_tokens, seed=0, quant=quant)
     seqs = [SeqInit(slot=i, prompt=prompts[i], pages=list(range(1 + pages_per * i, 1 + pages_per * (i + 1))),
                     temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=i) for i in range(total)]
     r.prefill(seqs)
