@@ -2,6 +2,7 @@
 group's graph (spin-wait on the upstream flag + compute) and the gaps between graphs."""
 import os
 os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")     # no checkpoints offline: random-init weights
+os.environ["B2B_GRAPH_PER_GROUP"] = "1"          # one graph per group so that a group-stage can be bracketed by events (production: one graph per step)
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,7 +40,7 @@ for s in range(4, STEPS):
     for g in range(groups):
         if g + 1 < groups:
             gaps.append(start[s][g + 1] - (start[s][g] + dur[s][g]))
-info = {"rank": rank, "layers": len(r.layers), "graph_us_mean": sum(flat) / len(flat), "graph_us_min": min(flat),
+info = {"rank": rank, "units": list(r.units), "launches": r.launches_per_decode_step(), "graph_us_mean": sum(flat) / len(flat), "graph_us_min": min(flat),
         "graph_us_max": max(flat), "gap_us_mean": sum(gaps) / max(1, len(gaps)), "per_step_us": (start[-1][0] - start[4][0]) / (STEPS - 5),
         "total_us": end_total}
 out = [None] * world
