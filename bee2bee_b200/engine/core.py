@@ -194,6 +194,7 @@ class Engine:
         self._cancelled: List[int] = []            # rids cancelled since the last step (rank 0 -> plan broadcast)
         self._wake = threading.Event()
         self._stop = False
+        self.broken: Optional[str] = None          # set once the mesh aborted (MeshStalled): the engine refuses new work
         self._thread: Optional[threading.Thread] = None
         self.host_ms = {"prefill": 0.0, "decode": 0.0, "collect": 0.0}     # host wall time per scheduler phase
         self._ttfts: "collections.deque[float]" = collections.deque(maxlen=4096)   # submit -> first token, ms
@@ -209,6 +210,14 @@ class Engine:
         if params.max_new_tokens > budget:
             params = SamplingParams(**{**params.__dict__, "max_new_tokens": max(1, budget)})
         r = Request(next(self._ids), ids, params, on_token, t_submit=time.time())
+        if self.broken:
+            # reference semantics for a lost peer: the provider disappears and the caller is told at once
+            # (/root/reference/bee2bee/p2p_runtime.py:396-410) -- no request may queue behind a dead mesh
+            r.error = self.broken
+            r.finish_reason = "error"
+            r.t_done = time.time()
+            r.done.set()
+            return r
         self._waiting.put(r)
         self._wake.set()
         return r
@@ -218,7 +227,12 @@ class Engine:
         reqs = [self.submit(p, params) for p in prompts]
         if self._thread is None:
             while not all(r.done.is_set() for r in reqs):
-                self.step()
+                try:
+                    self.step()
+                except Exception as e:
+                    self._note_failure(e)
+                    self._fail_all(f"engine error: {e!r}")
+                    raise
         return [r.wait().out_ids for r in reqs]
 
     def cancel(self, req: Request, reason: str = "cancelled") -> None:
@@ -262,7 +276,7 @@ class Engine:
                 "prefill_tokens": self.stats["prefill_tokens"], "decode_steps": self.stats["steps"],
                 "tokens_per_s": self.stats["tokens"] / busy, "running": len(self._running),
                 "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
-                "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
+                "healthy": self.broken is None, "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
                 "d2h_bytes": self.d2h_bytes, "native_launches": getattr(self.runner, "kernel_launches", 0),
                 "host_ms": dict(self.host_ms),
                 "ttft_ms": ({"count": len(self._ttfts), "p50": statistics.median(self._ttfts),
@@ -276,6 +290,7 @@ class Engine:
                 worked = self.step()
             except Exception as e:  # keep serving: fail the in-flight requests, not the node
                 worked = True
+                self._note_failure(e)                 # first: waiters woken by _fail_all must already see `broken`
                 self._fail_all(f"engine error: {e!r}")
             if not worked:
                 self._wake.wait(0.05)
@@ -310,6 +325,19 @@ class Engine:
         while not self._stop:
             if not self.step():
                 time.sleep(0.002)
+
+    def _note_failure(self, exc: Exception) -> None:
+        from .runner import MeshStalled
+
+        if isinstance(exc, MeshStalled):
+            self.broken = f"mesh unavailable: {exc}"
+            while True:                      # nobody may wait on a queue that will never be served
+                try:
+                    r = self._waiting.get_nowait()
+                except queue.Empty:
+                    break
+                r.error, r.finish_reason, r.t_done = self.broken, "error", time.time()
+                r.done.set()
 
     def _fail_all(self, msg: str) -> None:
         for r in list(self._running.values()) + self._pending:

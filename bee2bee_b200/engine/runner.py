@@ -53,6 +53,11 @@ def _pow2_at_least(n: int, lo: int = 1) -> int:
     return v
 
 
+class MeshStalled(RuntimeError):
+    """A bounded device-side wait on a peer's flag gave up (late / hung / dead rank): the results of the burst are
+    garbage and the mesh epochs are no longer aligned.  The process and its CUDA context are intact."""
+
+
 class _HostRing:
     """Mapped pinned host memory (cudaHostAlloc) visible to kernels by address and to the host as a tensor."""
 
@@ -154,6 +159,16 @@ class GpuRunner:
         self._win_width = 0
         self._fetch_ev = torch.cuda.Event()
         self.C.init_kernels(self.device.index)
+        # bounded handoff waits: a peer that does not publish within the limit raises the (device-resident) abort word
+        # instead of trapping the GPU; fetch_window reports it through a mapped host word.  B2B_WAIT_TIMEOUT_MS=0 -> trap.
+        self.wait_timeout_ms = float(os.environ.get("B2B_WAIT_TIMEOUT_MS", "30000"))
+        self.aborted = False
+        self._status = _HostRing(self.C, 16)
+        self._status.view.zero_()
+        self._abort_word = self.C.peer_alloc(256)
+        self.C.tensor_from_ptr(self._abort_word, [64], "i32", self.device.index).zero_()
+        torch.cuda.synchronize(self.device)
+        self.C.set_wait_policy(self._abort_word if self.wait_timeout_ms > 0 else 0, self.wait_timeout_ms)
         if world == 1:
             self.warmup()
         self._ensure_graphs()
@@ -210,9 +225,10 @@ class GpuRunner:
         and sequence cost ~25 ms for 256 admissions)."""
         dev, i32 = self.device, torch.int32
         S = len(seqs)
-        bt_host = torch.zeros((S, self.max_pages_per_seq), dtype=i32)
+        bt_np = np.zeros((S, self.max_pages_per_seq), dtype=np.int32)
         for i, s in enumerate(seqs):
-            bt_host[i, :len(s.pages)] = torch.tensor(s.pages, dtype=i32)
+            bt_np[i, :len(s.pages)] = s.pages
+        bt_host = torch.from_numpy(bt_np)
         fl_host = torch.tensor([[s.temperature, s.top_p, s.repetition_penalty] for s in seqs], dtype=torch.float32)
         seed_host = torch.tensor([int(s.seed) & 0x7FFFFFFF for s in seqs], dtype=i32)
         rows = torch.tensor([s.slot for s in seqs], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
@@ -226,11 +242,11 @@ class GpuRunner:
         self.seen.index_fill_(0, rows, 0)
         self.h2d_bytes += bt_host.numel() * 4 + fl_host.numel() * 4 + S * (4 + 8)
         if self.last:
-            flat = [t for s in seqs for t in s.prompt]
+            flat = np.concatenate([np.asarray(s.prompt, dtype=np.int32) for s in seqs])
+            owner = np.repeat(np.asarray([s.slot for s in seqs], dtype=np.int32), [len(s.prompt) for s in seqs])
             self.h2d_bytes += 8 * len(flat)
-            owner = [s.slot for s in seqs for _ in s.prompt]
-            ops.mark_seen(torch.tensor(flat, dtype=i32).pin_memory().to(dev, non_blocking=True),
-                          torch.tensor(owner, dtype=i32).pin_memory().to(dev, non_blocking=True), self.seen,
+            ops.mark_seen(torch.from_numpy(flat).pin_memory().to(dev, non_blocking=True),
+                          torch.from_numpy(owner).pin_memory().to(dev, non_blocking=True), self.seen,
                           self.cfg.vocab_size)
 
     def _pack(self, seqs: Sequence[SeqInit]) -> List[List[Tuple[SeqInit, int, int]]]:
@@ -503,9 +519,13 @@ class GpuRunner:
         hist = self.mesh.hist_base() if self.world > 1 else self.history.data_ptr()
         with torch.cuda.stream(self.stream):
             self.C.fetch_window(hist, self.hist_len, self._cur.dev_ptr, B, width, self._win.dev_ptr, self._waits.dev_ptr,
-                                n_waits)
+                                n_waits, self._status.dev_ptr)
             self._fetch_ev.record(self.stream)
         self._fetch_ev.synchronize()
+        if int(self._status.view[0]) != 0:
+            self.aborted = True
+            raise MeshStalled(f"rank {self.rank}: a peer piece did not publish its handoff flag within "
+                              f"{self.wait_timeout_ms:.0f} ms; the burst was drained and discarded")
         self.h2d_bytes += B * 4 + n_waits * 16
         self.d2h_bytes += B * width * 4
         return self._win.view[:B * width].view(B, width).clone()
@@ -531,7 +551,12 @@ class GpuRunner:
     def close(self) -> None:
         self.graphs.clear()
         self._pf.clear()
-        for r in (self._cur, self._waits, self._win):
+        for r in (self._cur, self._waits, self._win, self._status):
             if r is not None:
                 r.free()
+        try:
+            self.C.set_wait_policy(0, 0.0)
+            self.C.peer_free(self._abort_word)
+        except Exception:
+            pass
         self.mesh.close()

@@ -127,6 +127,13 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
 }
 
+// Bounded handoff waits (call once per device after peer_alloc'ing the abort word): limit_ms == 0 restores "trap".
+void set_wait_policy(int64_t abort_word, double limit_ms) {
+  const auto ns = static_cast<unsigned long long>(limit_ms * 1e6);
+  check(b2b::set_wait_policy_gemm(as_ptr<uint32_t>(abort_word), ns), "set_wait_policy(gemm)");
+  check(b2b::set_wait_policy_elementwise(as_ptr<uint32_t>(abort_word), ns), "set_wait_policy(elementwise)");
+}
+
 void set_pdl(bool on) { b2b::g_pdl_mode = on ? 1 : 0; }
 bool get_pdl() { return b2b::pdl_enabled(); }
 
@@ -323,10 +330,11 @@ void set_decode_state(const Tensor& positions, const Tensor& kv_len, const Tenso
 
 // history / cursors / out / waits are raw addresses: the ring may be peer memory, the rest mapped pinned host memory
 void fetch_window(int64_t history, int64_t hist_stride, int64_t cursors, int64_t rows, int64_t width, int64_t out,
-                  int64_t waits, int64_t n_waits) {
+                  int64_t waits, int64_t n_waits, int64_t status) {
   check(b2b::launch_fetch_window(as_ptr<const int>(history), static_cast<int>(hist_stride), as_ptr<const int>(cursors),
                                  static_cast<int>(rows), static_cast<int>(width), as_ptr<int>(out),
-                                 as_ptr<const b2b::FlagWait>(waits), static_cast<int>(n_waits), cur_stream()),
+                                 as_ptr<const b2b::FlagWait>(waits), static_cast<int>(n_waits), as_ptr<int>(status),
+                                 cur_stream()),
         "fetch_window");
 }
 
@@ -411,6 +419,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mark_seen", &mark_seen);
   m.def("set_decode_state", &set_decode_state);
   m.def("fetch_window", &fetch_window);
+  m.def("set_wait_policy", &set_wait_policy);
   m.def("peer_alloc", &peer_alloc);
   m.def("peer_free", &peer_free);
   m.def("ipc_export", &ipc_export);

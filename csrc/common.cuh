@@ -304,12 +304,44 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Spin until *flag >= target (monotonic counters; wrap-safe compare).
+// Mesh abort word (device memory, one per process / GPU; set through set_wait_policy() of every translation unit that
+// waits on handoff flags).  A wait that exceeds the time bound does NOT trap the GPU (round 1: a late or dead peer took
+// all 8 contexts down): it raises the abort word and returns; every later wait of this process returns at once, so the
+// pipeline drains with garbage in microseconds, the token read-back kernel reports the word to the host and the engine
+// fails the in-flight requests with a clean error while the process (and its control plane) stays alive.
+static __device__ uint32_t* g_abort_word = nullptr;
+static __device__ unsigned long long g_wait_limit_ns = 0;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *flag >= target (monotonic counters; wrap-safe compare); bounded, see above.
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t target) {
+  if (static_cast<int32_t>(ld_acquire_sys(flag) - target) >= 0) return;          // fast path: already published
+  volatile uint32_t* ab = g_abort_word;
+  if (ab != nullptr && *ab != 0u) return;                                        // mesh aborted: drain
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (static_cast<int32_t>(ld_acquire_sys(flag) - target) < 0) {
     __nanosleep(20);
-    if (++spins > B2B_SPIN_LIMIT) { __trap(); }
+    ++spins;
+    if (ab != nullptr) {
+      if ((spins & 127u) == 0u) {
+        if (*ab != 0u) return;                                                   // another waiter gave up
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > g_wait_limit_ns) {
+          *ab = 1u;
+          __threadfence_system();
+          return;
+        }
+      }
+    } else if (spins > B2B_SPIN_LIMIT) {
+      __trap();
+    }
   }
 }
 

@@ -341,11 +341,15 @@ __global__ void set_decode_state_kernel(int* positions, int* kv_len, int* q_len,
 // prefill-done flag; the flags and the history ring may live on rank 0 = peer memory for follower ranks) and gathers
 // every sequence's new tokens straight into mapped pinned host memory -- no NCCL broadcast, no host barrier.
 __global__ void fetch_window_kernel(const int* history, int hist_stride, const int* cursors, int width, int* out,
-                                    const FlagWait* waits, int n_waits) {
+                                    const FlagWait* waits, int n_waits, int* status) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_waits; ++i) wait_flag_ge(waits[i].flag, waits[i].target);
+    if (blockIdx.x == 0 && status != nullptr) {
+      volatile uint32_t* ab = g_abort_word;
+      *status = (ab != nullptr && *ab != 0u) ? 1 : 0;        // mapped host word: did any bounded wait give up?
+    }
   }
   __syncthreads();
   const int b = blockIdx.x;
@@ -362,9 +366,10 @@ int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* 
   return static_cast<int>(cudaGetLastError());
 }
 int launch_fetch_window(const int* history, int hist_stride, const int* cursors, int rows, int width, int* out,
-                        const FlagWait* waits, int n_waits, cudaStream_t s) {
+                        const FlagWait* waits, int n_waits, int* status, cudaStream_t s) {
   if (rows <= 0 || width <= 0) return 0;
-  launch_kernel(fetch_window_kernel, dim3(rows), dim3(64), 0, s, 1, history, hist_stride, cursors, width, out, waits, n_waits);
+  launch_kernel(fetch_window_kernel, dim3(rows), dim3(64), 0, s, 1, history, hist_stride, cursors, width, out, waits, n_waits,
+                status);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
@@ -433,6 +438,12 @@ int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta
 int launch_flag_signal(uint32_t* flag, uint32_t* epoch, uint32_t* bump_epoch, uint32_t* ack_flag, cudaStream_t s) {
   launch_kernel(flag_signal_kernel, dim3(1), dim3(1), 0, s, 1, flag, epoch, bump_epoch, ack_flag);
   return static_cast<int>(cudaGetLastError());
+}
+
+int set_wait_policy_elementwise(uint32_t* abort_word, unsigned long long limit_ns) {
+  cudaError_t e = cudaMemcpyToSymbol(g_abort_word, &abort_word, sizeof(abort_word));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_wait_limit_ns, &limit_ns, sizeof(limit_ns));
+  return static_cast<int>(e);
 }
 
 }  // namespace b2b

@@ -778,4 +778,10 @@ int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn,
   }
 }
 
+int set_wait_policy_gemm(uint32_t* abort_word, unsigned long long limit_ns) {
+  cudaError_t e = cudaMemcpyToSymbol(g_abort_word, &abort_word, sizeof(abort_word));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_wait_limit_ns, &limit_ns, sizeof(limit_ns));
+  return static_cast<int>(e);
+}
+
 }  // namespace b2b

@@ -51,8 +51,12 @@ int launch_set_decode_state(int* positions, int* kv_len, int* q_len, const int* 
 // token-window read-back: wait for up to `n_waits` (flag, target) pairs, then out[b, j] = history[b, (cursor[b] + j) % stride]
 struct FlagWait { const uint32_t* flag; uint32_t target; uint32_t pad; };
 int launch_fetch_window(const int* history, int hist_stride, const int* cursors, int rows, int width, int* out,
-                        const FlagWait* waits, int n_waits, cudaStream_t s);
+                        const FlagWait* waits, int n_waits, int* status, cudaStream_t s);
 int launch_mark_seen(const int* ids, const int* seq_of, uint32_t* seen, int n, int vocab, cudaStream_t s);
+
+// bounded handoff waits: device abort word + time limit for the waits of each translation unit (0 / null = trap policy)
+int set_wait_policy_gemm(uint32_t* abort_word, unsigned long long limit_ns);
+int set_wait_policy_elementwise(uint32_t* abort_word, unsigned long long limit_ns);
 
 // gemm_tc.cu
 int gemm_tc_max_splitk(int bn, int epi, int stages);

@@ -330,3 +330,23 @@ def test_weights_policy_random_init_is_opt_in(monkeypatch, tmp_path):
         ModelConfig.from_hf_dict({**base, "attention_bias": True})
     with pytest.raises(ValueError):
         ModelConfig.from_hf_dict({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+
+
+def test_engine_marks_itself_broken_when_the_mesh_stalls():
+    """a peer piece that stops answering must fail the in-flight requests and take the provider out of
+    service (the reference drops the peer, p2p_runtime.py:396-410) -- not hang or kill the node."""
+    from bee2bee_b200.engine.runner import MeshStalled
+
+    eng = Engine("tiny-llama", device="cpu", max_batch=2, max_seq_len=64)
+    real = eng.runner.decode
+    eng.runner.decode = lambda n: (_ for _ in ()).throw(MeshStalled("rank 0: a peer piece did not publish"))
+    eng.start()
+    r = eng.submit([1, 2, 3], SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))
+    with pytest.raises(RuntimeError):
+        r.wait(timeout=30)
+    assert "engine error" in r.error and eng.broken and not eng.metrics()["healthy"]
+    late = eng.submit([4, 5], SamplingParams(max_new_tokens=2))
+    assert late.done.is_set() and "mesh unavailable" in late.error           # refused at once, nothing queues
+    assert not eng._running and eng.alloc.free_pages == eng.alloc.num_pages - 1
+    eng.stop()
+    eng.runner.decode = real

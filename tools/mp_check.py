@@ -61,6 +61,30 @@ else:
     seqs = [SeqInit(slot=i, prompt=prompts[i], pages=list(range(1 + pages_per * i, 1 + pages_per * (i + 1))),
                     temperature=0.0, top_p=1.0, repetition_penalty=1.0, seed=i) for i in range(total)]
     r.prefill(seqs)
+    stall = float(os.environ.get("B2B_FAULT_STALL_S", "0"))
+    if stall and rank == int(os.environ.get("B2B_FAULT_STALL_RANK", "1")):
+        import time
+        time.sleep(stall)                 # fault injection: this rank is late by `stall` seconds
+    if stall:
+        from bee2bee_b200.engine.runner import MeshStalled
+        import time
+        t0 = time.time()
+        try:
+            r.decode(steps // 2)
+            r.sync()
+            outcome = {"stalled": False}
+        except MeshStalled as e:
+            outcome = {"stalled": True, "after_s": round(time.time() - t0, 2), "error": str(e)[:80]}
+        # the process survived: CUDA still works on this rank
+        outcome["cuda_ok"] = bool(torch.ones(4, device=f"cuda:{local}").sum().item() == 4.0)
+        import torch.distributed as dist
+        gathered = [None] * world
+        dist.all_gather_object(gathered, outcome)
+        if rank == 0:
+            print("RESULT " + json.dumps({"world": world, "tokens": gathered}), flush=True)
+        r.close()
+        shutdown()
+        sys.exit(0)
     r.decode(steps // 2)
     r.sync()
     r.decode(steps - steps // 2)          # second burst: epochs are monotonic, nothing is re-armed in between
