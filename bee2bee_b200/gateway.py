@@ -257,8 +257,15 @@ def create_app(bridge: Optional[MeshBridge] = None, metrics: Optional[MetricsSto
 
     @app.get("/", response_class=HTMLResponse)
     def page() -> str:
+        """The web console (landing / quick-register / dashboard / chat, bee2bee_b200/web/index.html; the reference's
+        React SPA, /root/reference/app/src/App.jsx, talks to the same /api/p2p/* routes).  ``?link=`` pre-fills the
+        register form.  Falls back to the built-in minimal chat page when the static file is not installed."""
         state["metrics"].add(visits=1)
-        return _PAGE
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "web", "index.html"), encoding="utf-8") as f:
+                return f.read()
+        except OSError:
+            return _PAGE
 
     @app.post("/api/p2p/register")
     async def register(req: Request):

@@ -110,7 +110,7 @@ def test_register_status_generate_metrics(gateway):
         "status": "discovery_initiated"}
     nf = c.get("/api/p2p/nope")
     assert nf.status_code == 404 and "not found" in nf.json()["error"]
-    assert "mesh gateway" in c.get("/").text
+    assert "mesh console" in c.get("/").text
 
 
 def test_generate_without_any_node_reports_error_in_stream(tmp_path, monkeypatch):
@@ -119,3 +119,12 @@ def test_generate_without_any_node_reports_error_in_stream(tmp_path, monkeypatch
         r = c.post("/api/p2p/generate", json={"prompt": "hi"})
         assert r.status_code == 200 and "[Error]: no_node_available" in r.text
         assert c.get("/api/p2p/global_metrics").json() == {"visits": 0, "chats": 0, "tokens": 0}
+
+
+def test_web_console_page_is_served(gateway):
+    """C21: landing / quick-register / dashboard / chat console; same /api/p2p/* routes as the reference's SPA."""
+    client = gateway[0] if isinstance(gateway, (tuple, list)) else gateway
+    page = client.get("/").text
+    for needle in ("parseJoinLink", "/api/p2p/register", "/api/p2p/generate", "/api/p2p/status", "/api/p2p/global_metrics",
+                   "setInterval(refresh,15000)", "user", "assistant:", "URLSearchParams(location.search)"):
+        assert needle in page, needle
