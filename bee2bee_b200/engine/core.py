@@ -340,10 +340,7 @@ class Engine:
                 r.done.set()
 
     def _fail_all(self, msg: str) -> None:
-        for r in list(self._running.values()) + self._pending:
-            r.error = msg
-            r.t_done = time.time()
-            r.done.set()
+        victims = list(self._running.values()) + self._pending
         try:
             self.runner.release(list(self._running.keys()))
         except Exception:
@@ -353,6 +350,10 @@ class Engine:
             self._free_slots.append(b)
         self._running.clear()
         self._pending.clear()
+        for r in victims:          # wake the waiters last: they may inspect the engine state right away
+            r.error = msg
+            r.t_done = time.time()
+            r.done.set()
 
     def step(self) -> bool:
         """One scheduler iteration: retire cancelled requests, admit + prefill, then one decode burst.

@@ -19,6 +19,7 @@ of the reference (/root/reference/bee2bee/hf.py:180-205, bee2bee/node.py:249-277
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -97,6 +98,7 @@ class NativePiece:
         # operands, applied by the tensor core (tcgen05 kind::mxf8f6f4.block_scale).
         self.fp8 = quant in ("fp8", "mxfp8") and self.fused_norm and not cfg.post_norms and cfg.glu
         self.mx = self.fp8 and quant == "mxfp8"
+        self.mx_fuse = False
         self.wscale: Dict[str, torch.Tensor] = {}
         c = cfg
         assert c.hidden_size % 128 == 0 or c.hidden_size % 64 == 0, "hidden must be a multiple of 64"
@@ -162,9 +164,23 @@ class NativePiece:
             self._qbuf = {k: torch.zeros((rows, k), device=self.device, dtype=torch.float8_e4m3fn) for k in widths}
             self._qscale = torch.zeros(rows, device=self.device, dtype=torch.float32)
             if self.mx:
-                # activation scale-factor chunks: worst case is 32-row tiles (512 B per tile and 128 K)
+                # activation scale-factor chunks: worst case is 32-row tiles (512 B per tile and 128 K); 127 = 2^0 for
+                # rows nobody writes (0xFF would be NaN)
                 tiles = (rows + 31) // 32
-                self._qsf = {k: torch.zeros(tiles * (k // 128) * 512, device=self.device, dtype=torch.uint8) for k in widths}
+                self._qsf = {k: torch.full((tiles * (k // 128) * 512,), 127, device=self.device, dtype=torch.uint8)
+                             for k in widths}
+                # fused quantisation (B2B_MX_FUSE, default on): the O / down epilogues emit the e4m3 copy of the residual
+                # stream for the next RMSNorm-fused GEMM (+ per-token sum of squares), the gate/up epilogue emits the
+                # e4m3 MLP hidden for the down GEMM -- 3 of the 4 activation-quantiser launches of a layer disappear
+                self.mx_fuse = os.environ.get("B2B_MX_FUSE", "1") == "1"
+                H, F = cfg.hidden_size, cfg.ffn_size
+                self._fq_x = torch.zeros((rows, H), device=self.device, dtype=torch.float8_e4m3fn)
+                self._fq_h = torch.zeros((rows, F), device=self.device, dtype=torch.float8_e4m3fn)
+                self._fq_sf_x = torch.full((tiles * (H // 128) * 512,), 127, device=self.device, dtype=torch.uint8)
+                self._fq_sf_h = torch.full((tiles * (F // 128) * 512,), 127, device=self.device, dtype=torch.uint8)
+                self._sumsq1 = torch.zeros(rows, device=self.device, dtype=torch.float32)   # stream entering an attention block
+                self._sumsq2 = torch.zeros(rows, device=self.device, dtype=torch.float32)   # stream entering an MLP block
+                self._sumsq_head = torch.zeros(rows, device=self.device, dtype=torch.float32)  # separate-kernel quantiser (piece heads, lm_head)
 
         # ---- KV cache: one [pages, 64, n_kv, D] pair per layer whose attention block runs on this piece
         self.k_cache = {l: torch.zeros((num_pages, ops.PAGE, c.n_kv_heads, c.head_dim), device=dev, dtype=bf)
@@ -225,6 +241,11 @@ class NativePiece:
         fp8: per-token scale [x 1/rms] rides in ``rstd``; mxfp8: 1/rms is folded into the quantised values and the
         UE8M0 scale-factor chunks go to ``sfb``."""
         T, K = x.shape
+        if self.mx and self.mx_fuse and with_rms:
+            # same numerics as the epilogue-fused quantisation: raw values, 1/rms applied by the consuming GEMM
+            ss = self._sumsq_head[:T]
+            xq, sfb = ops.quant_mxfp8_rows(x, 0, self.cfg.norm_eps, out=self._qbuf[K][:T], sf_out=self._qsf[K], sumsq_out=ss)
+            return xq, {"sfb": sfb, "sumsq": ss}
         if self.mx:
             xq, sfb = ops.quant_mxfp8_rows(x, 0, self.cfg.norm_eps, with_rms, out=self._qbuf[K][:T], sf_out=self._qsf[K])
             return xq, {"sfb": sfb}
@@ -271,6 +292,9 @@ class NativePiece:
             wait_flag, wait_epoch = hand.in_flag, hand.in_epoch
         inline = self._use_inline_rstd(T)
         n_layers = len(self.layers)
+        fuse = self.mx_fuse
+        q_bn = ops.pick_bn_mx(T) if fuse else 0
+        xq_ready = False       # the residual stream entering the next attention block has a fused e4m3 copy (+ sumsq1)
         for li, l in enumerate(self.layers):
             p = f"l{l}."
             do_attn, do_gu, do_down = self.has_attn(l), self.has_gu(l), self.has_down(l)
@@ -299,7 +323,12 @@ class NativePiece:
                               v_cache=self.v_cache[l], positions=m.positions, slots=m.slots, n_q_heads=c.n_heads,
                               n_kv_heads=c.n_kv_heads, head_dim=c.head_dim, rope_theta=c.rope_theta,
                               q_scale=c.softmax_scale)
-                if self.fp8:
+                if self.fp8 and xq_ready:
+                    # e4m3 copy + scale factors + sum of squares were produced by the previous layer's down epilogue
+                    ops.gemm(self.w[p + "wqkv"], self._fq_x[:T], sfb=self._fq_sf_x, sumsq=self._sumsq1,
+                             **self._wkw(p + "wqkv"), **qkv_kw)
+                    xq_ready = False
+                elif self.fp8:
                     if head_wait and inline:
                         ops.native().flag_wait(head_wait, head_epoch, 1)     # the quant kernel reads x first
                     xq, akw = self._quant(x, with_rms=True)
@@ -334,8 +363,14 @@ class NativePiece:
                     ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
                 elif self.fp8:
                     aq, akw = self._quant(a, with_rms=False)
+                    x2_fused = fuse and do_gu and do_down          # this layer's gate/up and down run here
+                    fq = {}
+                    if fuse:
+                        fq = dict(zero_buf=self._sumsq1)
+                        if x2_fused:
+                            fq.update(fq_out=self._fq_x[:T], fq_sf=self._fq_sf_x, fq_bn=q_bn, sumsq_out=self._sumsq2)
                     ops.gemm(self.w[p + "wo"], aq, out=o_out, epi=ops.EPI_RESIDUAL, residual=x, **akw,
-                             **self._wkw(p + "wo"), **okw)
+                             **self._wkw(p + "wo"), **okw, **fq)
                 else:
                     ops.gemm(self.w[p + "wo"], a, out=o_out, epi=ops.EPI_RESIDUAL, residual=x, bias=self.w.get(p + "bo"),
                              **okw)
@@ -350,12 +385,19 @@ class NativePiece:
             gu_tail = tail_kw if (do_gu and not do_down) else {}   # piece ends after gate/up: it is the tail GEMM
             if gu_tail and hand.out_h:
                 gu_tail = dict(gu_tail, out_ptr=hand.out_h, ld_out=c.ffn_size)
+            h_fused = False
             if not do_gu:
                 hmid = h_in[:T]                              # the upstream piece ran gate/up: staged MLP hidden
             elif c.glu and self.fp8:
-                x2q, akw = self._quant(x2, with_rms=True)
-                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=None if gu_tail else self.h_buf[:T], epi=ops.EPI_GLU, **akw,
-                                **self._wkw(p + "wgu"), act_gelu=(c.act == "gelu_tanh"), **gu_tail)
+                h_fused = fuse and do_down and not gu_tail   # the down GEMM of this layer consumes the e4m3 hidden directly
+                hq_kw = dict(fq_out=self._fq_h[:T], fq_sf=self._fq_sf_h, fq_bn=q_bn, no_out=True) if h_fused else {}
+                if fuse and do_attn and do_down and not c.post_norms:
+                    # x2 was quantised by the O-proj epilogue of this layer (sum of squares in sumsq2)
+                    x2q, akw = self._fq_x[:T], dict(sfb=self._fq_sf_x, sumsq=self._sumsq2)
+                else:
+                    x2q, akw = self._quant(x2, with_rms=True)
+                hmid = ops.gemm(self.w[p + "wgu"], x2q, out=None if (gu_tail or h_fused) else self.h_buf[:T], epi=ops.EPI_GLU,
+                                eps=eps, **akw, **self._wkw(p + "wgu"), act_gelu=(c.act == "gelu_tanh"), **gu_tail, **hq_kw)
             elif c.glu:
                 r2 = None
                 if self.fused_norm and not inline:
@@ -388,9 +430,19 @@ class NativePiece:
                 if not do_attn and xn.data_ptr() == x2.data_ptr():
                     xn = self.xb[:T]    # x2 aliases the input buffer here: keep the residual source intact
                 if self.fp8:
-                    hq, akw = self._quant(hmid, with_rms=False)
+                    if h_fused:
+                        hq, akw = self._fq_h[:T], dict(sfb=self._fq_sf_h)
+                    else:
+                        hq, akw = self._quant(hmid, with_rms=False)
+                    fq = {}
+                    if fuse:
+                        fq = dict(zero_buf=self._sumsq2)
+                        if li + 1 < n_layers and not tail_kw:
+                            # the next layer's QKV GEMM (on this piece) reads the e4m3 copy; its RMSNorm uses sumsq1
+                            fq.update(fq_out=self._fq_x[:T], fq_sf=self._fq_sf_x, fq_bn=q_bn, sumsq_out=self._sumsq1)
+                            xq_ready = True
                     ops.gemm(self.w[p + "w_down"], hq, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
-                             residual=x2, **akw, **self._wkw(p + "w_down"), **tail_kw)
+                             residual=x2, **akw, **self._wkw(p + "w_down"), **tail_kw, **fq)
                 else:
                     ops.gemm(self.w[p + "w_down"], hmid, out=None if tail_kw else xn, epi=ops.EPI_RESIDUAL,
                              residual=x2, bias=self.w.get(p + "b_down"), wait_flag=down_wait, wait_epoch=down_epoch,
@@ -412,7 +464,7 @@ class NativePiece:
             ops.native().flag_signal(0, 0, hand.in_epoch, hand.up_ack)
         if self.fused_norm and self.fp8 and "lm_head" in self.wscale:
             lq, akw = self._quant(xl, with_rms=True)
-            ops.gemm(self.w["lm_head"], lq, out=self.logits[:S], epi=ops.EPI_PLAIN, **akw, **self._wkw("lm_head"),
+            ops.gemm(self.w["lm_head"], lq, out=self.logits[:S], epi=ops.EPI_PLAIN, eps=eps, **akw, **self._wkw("lm_head"),
                      out_fp32=True)
         elif self.fused_norm:
             ops.gemm(self.w["lm_head"], xl, out=self.logits[:S], epi=ops.EPI_PLAIN, norm_from_x=True, eps=eps,

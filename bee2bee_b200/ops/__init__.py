@@ -159,7 +159,10 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
          done_counter: int = 0, free_flag: int = 0, bump_epoch: int = 0, ack_flag: int = 0,
          dbg: int = 0, w_scale: Optional[torch.Tensor] = None,
          sfa: Optional[torch.Tensor] = None, sfb: Optional[torch.Tensor] = None, mc: int = -1, pf: int = -1,
-         stages: int = -1, free_lag: int = 0, out2_ptr: int = 0) -> Optional[torch.Tensor]:
+         stages: int = -1, free_lag: int = 0, out2_ptr: int = 0,
+         fq_out: Optional[torch.Tensor] = None, fq_sf: Optional[torch.Tensor] = None, fq_bn: int = 0,
+         sumsq_out: Optional[torch.Tensor] = None, zero_buf: Optional[torch.Tensor] = None,
+         sumsq: Optional[torch.Tensor] = None, no_out: bool = False) -> Optional[torch.Tensor]:
     """out[t, n] = epilogue(sum_k x[t, k] * w[n, k]) on the tcgen05 swap-AB kernel."""
     m_tok, k = x.shape
     n_out = w.shape[0]
@@ -176,8 +179,8 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
         stages = GEMM_STAGES if bn <= 64 else 0
     if splitk <= 0:
         splitk = pick_splitk(n_out, m_tok, k, bn, epi, stages)
-    if epi == EPI_QKV_ROPE:
-        o_ptr, ldo = 0, 0
+    if epi == EPI_QKV_ROPE or (no_out and fq_out is not None):
+        o_ptr, ldo = 0, 0          # no bf16 output: QKV writes q / KV cache; a GLU whose only consumer reads the fused e4m3 copy
     elif out_ptr:
         o_ptr, ldo = out_ptr, ld_out
     else:
@@ -198,7 +201,9 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
                   out_fp32, q_out, k_cache, v_cache, positions, slots, n_q_heads, n_kv_heads, head_dim, rope_theta,
                   q_scale, wait_flag, wait_epoch, signal_flag, signal_epoch, done_counter, free_flag, bump_epoch,
                   ack_flag, dbg, w_scale, sfa, sfb, GEMM_MC if mc < 0 else mc,
-                  L2_PREFETCH if pf < 0 else pf, stages, free_lag, out2_ptr)
+                  L2_PREFETCH if pf < 0 else pf, stages, free_lag, out2_ptr,
+                  _ptr(fq_out), _ptr(fq_sf), fq_out.shape[1] if fq_out is not None else 0, fq_bn, _ptr(sumsq_out), _ptr(zero_buf),
+                  _ptr(sumsq))
     return out
 
 
@@ -270,7 +275,8 @@ def mx_unchunk(sf_chunks: torch.Tensor, rows: int, K: int, bn: int = 128) -> tor
     return v[:, :bn].reshape(tiles * bn, nkc * 4)[:rows]
 
 
-def quant_mxfp8_rows(x: torch.Tensor, bn: int = 0, eps: float = 1e-5, with_rms: bool = False, out=None, sf_out=None):
+def quant_mxfp8_rows(x: torch.Tensor, bn: int = 0, eps: float = 1e-5, with_rms: bool = False, out=None, sf_out=None,
+                     sumsq_out=None):
     """Dynamic MX quantisation of GEMM activations (optionally fused with the RMSNorm 1/rms scale);
     returns (q, sf_chunks) for a GEMM whose token tile is ``bn`` (default: what ``gemm`` would pick)."""
     T, K = x.shape
@@ -281,7 +287,8 @@ def quant_mxfp8_rows(x: torch.Tensor, bn: int = 0, eps: float = 1e-5, with_rms: 
         out = torch.empty((T, K), device=x.device, dtype=torch.float8_e4m3fn)
     if sf_out is None:
         sf_out = torch.empty(tiles * (K // 128) * (1024 if bn > 128 else 512), device=x.device, dtype=torch.uint8)
-    native().quant_mxfp8_rows(x, out, sf_out, bn, eps, with_rms)
+    # sumsq_out: quantise the raw values and hand the row's sum of squares to the consuming GEMM (mode 2)
+    native().quant_mxfp8_rows(x, out, sf_out, bn, eps, 2 if sumsq_out is not None else int(bool(with_rms)), sumsq_out)
     return out, sf_out
 
 

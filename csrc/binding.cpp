@@ -46,7 +46,9 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
           // handoff
           int64_t wait_flag, int64_t wait_epoch, int64_t signal_flag, int64_t signal_epoch, int64_t done_counter,
           int64_t free_flag, int64_t bump_epoch, int64_t ack_flag, int64_t dbg, const OptT& w_scale,
-          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages, int64_t free_lag, int64_t out2_ptr) {
+          const OptT& sfa, const OptT& sfb, int64_t mc, int64_t pf_tiles, int64_t stages, int64_t free_lag, int64_t out2_ptr,
+          // fused MX quantisation of the output / RMSNorm statistics (raw addresses, 0 = off)
+          int64_t q_out8, int64_t q_sf, int64_t ld_q, int64_t q_bn, int64_t sumsq_out, int64_t zero_buf, int64_t sumsq) {
   const bool fp8 = w.scalar_type() == at::kFloat8_e4m3fn;
   if (fp8) {
     TORCH_CHECK(x.scalar_type() == at::kFloat8_e4m3fn && w.is_cuda() && x.is_cuda() && w.is_contiguous() &&
@@ -88,6 +90,15 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.out = as_ptr<void>(out_ptr);
   p.ld_out = static_cast<int>(ld_out);
   p.out2 = as_ptr<void>(out2_ptr);
+  p.q_out8 = as_ptr<uint8_t>(q_out8);
+  p.q_sf = as_ptr<uint8_t>(q_sf);
+  p.ld_q = static_cast<int>(ld_q);
+  p.q_bn = static_cast<int>(q_bn > 0 ? q_bn : 32);
+  p.sumsq_out = as_ptr<float>(sumsq_out);
+  p.zero_buf = as_ptr<float>(zero_buf);
+  p.sumsq = as_ptr<const float>(sumsq);
+  TORCH_CHECK(!p.q_out8 || (p.q_sf && p.ld_q % 128 == 0 && (epi == b2b::EPI_RESIDUAL || epi == b2b::EPI_GLU)),
+              "fused output quantisation: residual / GLU epilogues, scale-factor buffer and a row stride multiple of 128");
   p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
   p.ld_res = static_cast<int>(ld_res);
   p.bias = ptr_or_null<const float>(bias);
@@ -123,6 +134,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
     TORCH_CHECK(p.n_out == (p.n_q_heads + 2 * p.n_kv_heads) * p.head_dim, "qkv rows mismatch");
   }
   if (p.epi == b2b::EPI_RESIDUAL) TORCH_CHECK(p.residual != nullptr, "residual epilogue needs residual");
+  if (p.epi == b2b::EPI_GLU) TORCH_CHECK(p.out != nullptr || p.q_out8 != nullptr, "GLU epilogue needs an output");
   if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
   check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
 }
@@ -211,7 +223,8 @@ void quant_fp8_rows(const Tensor& x, const Tensor& q, const Tensor& scale_out, d
         "quant_fp8_rows");
 }
 
-void quant_mxfp8_rows(const Tensor& x, const Tensor& q, const Tensor& sf, int64_t bn, double eps, bool with_rms) {
+void quant_mxfp8_rows(const Tensor& x, const Tensor& q, const Tensor& sf, int64_t bn, double eps, int64_t with_rms,
+                      const OptT& sumsq_out) {
   check_bf16(x, "x");
   TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn && q.is_contiguous() && sf.scalar_type() == at::kByte &&
                   sf.is_contiguous(), "quant_mxfp8_rows: q must be float8_e4m3fn, sf uint8");
@@ -220,7 +233,8 @@ void quant_mxfp8_rows(const Tensor& x, const Tensor& q, const Tensor& sf, int64_
   const int tokens = static_cast<int>(x.numel() / h);
   TORCH_CHECK(sf.numel() >= ((tokens + bn - 1) / bn) * (h / 128) * (bn > 128 ? 1024 : 512), "quant_mxfp8_rows: sf too small");
   check(b2b::launch_quant_mxfp8_rows(x.data_ptr(), q.data_ptr(), sf.data_ptr(), tokens, h, static_cast<int>(bn),
-                                     static_cast<float>(eps), with_rms ? 1 : 0, cur_stream()),
+                                     static_cast<float>(eps), static_cast<int>(with_rms), ptr_or_null<float>(sumsq_out),
+                                     cur_stream()),
         "quant_mxfp8_rows");
 }
 

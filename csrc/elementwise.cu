@@ -231,8 +231,12 @@ __global__ void quant_fp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8
 // tcgen05.cp expects for a token tile of `bn` rows (see GemmParams::sfb).  One CTA per token; a warp
 // iteration covers 128 K elements (8 lanes x 4 elements = one 32-element block).  Padding rows of the last
 // tile get scale 2^0 (a 0xFF byte would be NaN).
+// with_rms: 0 = plain, 1 = 1/rms folded into the values before quantisation, 2 = values quantised as they are and the
+// row's sum of squares written to sumsq_out (the consuming GEMM applies 1/rms in its epilogue: same numerics as the
+// quantisation fused into a producing GEMM epilogue, csrc/gemm_tc.cu emit_q)
 __global__ void quant_mxfp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
-                                        uint8_t* __restrict__ sf, int tokens, int h, int bn, float eps, int with_rms) {
+                                        uint8_t* __restrict__ sf, int tokens, int h, int bn, float eps, int with_rms,
+                                        float* __restrict__ sumsq_out) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
@@ -257,7 +261,11 @@ __global__ void quant_mxfp8_rows_kernel(const __nv_bfloat16* __restrict__ x, uin
       ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
     }
     ss = block_sum(ss, sh);
-    rs = rsqrtf(ss / h + eps);
+    if (with_rms == 2) {
+      if (threadIdx.x == 0 && sumsq_out != nullptr) sumsq_out[t] = ss;
+    } else {
+      rs = rsqrtf(ss / h + eps);
+    }
   }
   uint32_t* qrow = reinterpret_cast<uint32_t*>(q + static_cast<size_t>(t) * h);
   for (int kc = warp; kc < nkc; kc += nw) {
@@ -423,12 +431,12 @@ int launch_quant_fp8_rows(const void* x, void* q, float* scale_out, int tokens, 
   return static_cast<int>(cudaGetLastError());
 }
 int launch_quant_mxfp8_rows(const void* x, void* q, void* sf, int tokens, int h, int bn, float eps, int with_rms,
-                            cudaStream_t s) {
+                            float* sumsq_out, cudaStream_t s) {
   if (h % 128 || bn < 32 || (bn & (bn - 1))) return -2;
   const int padded = (tokens + bn - 1) / bn * bn;
   launch_kernel(quant_mxfp8_rows_kernel, dim3(padded), dim3(h >= 4096 ? 512 : 256), 0, s, 1,
                 static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), tokens, h, bn, eps,
-                with_rms);
+                with_rms, sumsq_out);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s) {

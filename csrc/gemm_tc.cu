@@ -25,6 +25,8 @@
 // bee2bee/node.py:249-277 and the cuBLAS calls under bee2bee/hf.py:42-43.
 #include "gemm_tc.cuh"
 
+#include <cuda_fp8.h>
+
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -332,8 +334,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       } else {
         for (int t = col0 + et; t < col0 + ncol; t += 128) {
           const int tok = tok0 + t;
-          rstd_s[t] = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
+          float r = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
+          if (p.sumsq != nullptr && tok < p.m_tok)      // RMSNorm statistics accumulated by the producing GEMM's epilogue
+            r *= rsqrtf(p.sumsq[tok] / static_cast<float>(p.k) + p.eps);
+          rstd_s[t] = r;
         }
+        if (p.zero_buf != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
+          for (int t = et; t < BN; t += 128)
+            if (tok0 + t < p.m_tok) p.zero_buf[tok0 + t] = 0.f;
       }
       epi_bar_sync();
     }
@@ -411,6 +419,33 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
     }
 
+    // fused MX quantisation of one output value per lane (32 lanes = 32 consecutive features = one block) of token `tok`
+    const int q_nkc = p.ld_q >> 7;
+    const int q_chunk = p.q_bn > 128 ? 1024 : 512;
+    auto emit_q = [&](float val, int tok, int feat) {
+      const float r = bf16_round(val);                        // what a separate quantiser would read back from memory
+      float amax = fabsf(r);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      const uint32_t u = __float_as_uint(amax * (1.f / 448.f));
+      int e = static_cast<int>(u >> 23) - 127 + ((u & 0x7FFFFFu) ? 1 : 0);
+      e = max(-126, min(127, e));
+      const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+      p.q_out8[static_cast<size_t>(tok) * p.ld_q + feat] =
+          static_cast<uint8_t>(__nv_cvt_float_to_fp8(r * inv, __NV_SATFINITE, __NV_E4M3));
+      float ss = r * r;
+      if (p.sumsq_out != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (lane == 0) {
+        const int tile = tok / p.q_bn, n = tok - tile * p.q_bn, rr = n & 127;
+        p.q_sf[(static_cast<size_t>(tile) * q_nkc + (feat >> 7)) * q_chunk + (n >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4 +
+               ((feat >> 5) & 3)] = static_cast<uint8_t>(e + 127);
+        if (p.sumsq_out != nullptr) atomicAdd(&p.sumsq_out[tok], ss);
+      }
+    };
+
     // accumulators of up to 16 columns starting at local column c (slice-relative)
     auto load_acc = [&](int c, int n, float* v) {
       if (splitk == 1) {
@@ -485,15 +520,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] =
               __float2bfloat16_rn(gelu_tanh(a));
         } else if constexpr (EPI == EPI_RESIDUAL) {
-          const __nv_bfloat16 r16 = __float2bfloat16_rn(a + __bfloat162float(resid[i]));
+          const float rv = a + __bfloat162float(resid[i]);
+          const __nv_bfloat16 r16 = __float2bfloat16_rn(rv);
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
           if (p.out2 != nullptr)
             reinterpret_cast<__nv_bfloat16*>(p.out2)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
+          if (p.q_out8 != nullptr) emit_q(rv, tok, n_glob);
         } else if constexpr (EPI == EPI_GLU) {
           const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
-          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
-              __float2bfloat16_rn(g * u);
+          if (p.out != nullptr)
+            reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
+                __float2bfloat16_rn(g * u);
+          if (p.q_out8 != nullptr) emit_q(g * u, tok, tile_n * 64 + row);
         } else {   // EPI_QKV_ROPE
           float o = a;
           if (sect < 2 && p.rope_theta > 0.f) {

@@ -50,6 +50,18 @@ struct GemmParams {
   const __nv_bfloat16* norm_src;  // [m_tok, k] raw input (same tensor as X) or null
   float eps;
 
+  // Fused MX quantisation of the OUTPUT for the next GEMM (EPI_RESIDUAL / EPI_GLU): e4m3 values + UE8M0 scale per 32
+  // features in the consumer's scale-factor chunk layout (token tile q_bn), optional per-token sum of squares of the
+  // output (the consumer's RMSNorm: 1/rms is applied in ITS epilogue from `sumsq`), optional zeroing of the other
+  // norm point's accumulator.  A warp of the epilogue owns 32 consecutive output features = one MX block per token.
+  uint8_t* q_out8;                // [m_tok, ld_q] e4m3, or null
+  uint8_t* q_sf;                  // scale-factor chunks of the consumer GEMM's activation operand
+  int ld_q;                       // row stride of q_out8 in elements (= consumer K)
+  int q_bn;                       // consumer token tile (chunk layout), >= 32
+  float* sumsq_out;               // [m_tok] += sum over this CTA's features of out^2, or null
+  float* zero_buf;                // [m_tok] accumulator to clear (read by an earlier GEMM, re-filled by a later one), or null
+  const float* sumsq;             // consumer side: per-token sum of squares of X -> rstd = rsqrt(sumsq / k + eps)
+
   // EPI_QKV_ROPE
   __nv_bfloat16* q_out;           // [m_tok, n_q_heads*head_dim]
   __nv_bfloat16* k_cache;         // [slots, n_kv_heads, head_dim]

@@ -20,7 +20,7 @@ int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s
 int launch_quant_fp8_rows(const void* x, void* q, float* scale_out, int tokens, int h, float eps, int with_rms,
                           cudaStream_t s);
 int launch_quant_mxfp8_rows(const void* x, void* q, void* sf, int tokens, int h, int bn, float eps, int with_rms,
-                            cudaStream_t s);
+                            float* sumsq_out, cudaStream_t s);
 int launch_flag_wait(const uint32_t* flag, const uint32_t* epoch, uint32_t delta, cudaStream_t s);
 int launch_decode_advance(int* positions, int* kv_len, int* slots, const int* q_len, const int* block_table,
                           int max_pages, int n, cudaStream_t s);

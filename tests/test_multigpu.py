@@ -78,10 +78,17 @@ def test_two_gpu_engine_waves_match_single_gpu():
 def test_two_gpu_fp8_pipeline_matches_single_gpu(quant):
     """BASELINE config 3 shape: block-scaled (mxfp8) / per-row fp8 pieces across the NVLink handoff, incl. a cut
     between a gate/up and a down GEMM, equal the single-GPU fp8 engine token for token."""
-    kw = dict(B2B_QUANT=quant, B2B_STEPS="6")
+    kw = dict(B2B_QUANT=quant, B2B_STEPS="6", B2B_MX_FUSE="0")
     ref = _run(1, "tiny-llama", 2, 4, 0, **kw)
     assert _run(2, "tiny-llama", 2, 4, 29625, **kw) == ref
     assert _run(2, "tiny-llama", 2, 4, 29627, B2B_UNIT_BOUNDS="0,5,12", **kw) == ref
+    if quant == "mxfp8":
+        # epilogue-fused quantisation (default): RMSNorm statistics are accumulated with fp32 atomics, so runs are not
+        # bit-reproducible; the sequences must still agree almost everywhere with the single-GPU fused run
+        kw["B2B_MX_FUSE"] = "1"
+        a, b = _run(1, "tiny-llama", 2, 4, 0, **kw), _run(2, "tiny-llama", 2, 4, 29631, B2B_UNIT_BOUNDS="0,5,12", **kw)
+        same = sum(x == y for ra, rb in zip(a, b) for x, y in zip(ra, rb))
+        assert same >= 0.9 * sum(len(r) for r in a), (a, b)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
