@@ -340,8 +340,9 @@ def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, 
     CUDA-core split-KV kernel, and is faster even at 64 tokens (7.9 vs 10.1 us); few sequences with a long context
     keep the split-KV kernel (more CTAs than (sequence, kv head) pairs)."""
     if use_tc < 0 and max_q == 1:
-        seqs = q_len.shape[0]
-        use_tc = 1 if (seqs * n_kv >= 128 or splits <= 1) else 0
+        # split-KV (few sequences x long context) also runs on the tensor-core kernel: every (sequence, kv head, split) CTA
+        # streams its share of the pages, the shared merge pass combines the partials
+        use_tc = 1
     native().attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, ws, max_q, n_q, n_kv, head_dim,
                        window, softcap, splits, use_tc)
     return out

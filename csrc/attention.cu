@@ -303,6 +303,23 @@ int attention_init() {
   return 0;
 }
 
+int launch_attention_merge(void* out, const int* q_start, const float* ws, int seqs, int n_q, int n_kv, int head_dim,
+                           int splits, cudaStream_t s) {
+  AttnParams p{};
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.q_start = q_start;
+  p.ws = const_cast<float*>(ws);
+  p.n_q = n_q; p.n_kv = n_kv; p.splits = splits;
+  const int G = n_q / n_kv, R = attn_rows(G, 1);
+#define B2B_MERGE(DD, RR)                                                                                        \
+  if (head_dim == DD && R == RR)                                                                                  \
+    return static_cast<int>(launch_kernel(attn_merge_kernel<DD, RR>, dim3(seqs, n_kv), dim3(32 * (G < 1 ? 1 : G)), 0, s, 1, p, G));
+  B2B_MERGE(64, 4) B2B_MERGE(64, 8) B2B_MERGE(64, 16) B2B_MERGE(128, 4) B2B_MERGE(128, 8) B2B_MERGE(128, 16)
+  B2B_MERGE(256, 4) B2B_MERGE(256, 8) B2B_MERGE(256, 16)
+#undef B2B_MERGE
+  return -3;
+}
+
 int attn_rows(int G, int QB) {
   int r = G * QB;
   r = (r + 3) / 4 * 4;

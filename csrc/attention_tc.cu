@@ -42,6 +42,11 @@ struct AttnTcParams {
   const int* kv_len;
   int max_pages, n_q, n_kv, window;
   float softcap;
+  // split-KV decode (q_len == 1): grid.x = splits, CTA `split` covers a contiguous range of the 64-key tiles and writes
+  // its unnormalised partial (O, running max, row sum) to the workspace the CUDA-core kernel's merge pass reads:
+  // ws[((seq * n_kv + kvh) * splits + split) * ws_rows + head_in_group][D + 2]
+  int splits, ws_rows;
+  float* ws;
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -179,7 +184,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   pdl_launch_dependents();
   pdl_wait();                                               // the metadata below may come from an earlier kernel
   const int seq = blockIdx.z, kvh = blockIdx.y;
-  const int qblk = gridDim.x - 1 - blockIdx.x;             // longest (latest) query blocks first
+  const bool split_mode = p.splits > 1;
+  const int qblk = split_mode ? 0 : gridDim.x - 1 - blockIdx.x;   // longest (latest) query blocks first
   const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
   const int q0 = qblk * QB;
   if (q0 >= qlen) return;
@@ -188,7 +194,13 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int pos0 = kvlen - qlen + q0;                       // absolute position of query 0 of this block
   const int kv_hi = min(kvlen, pos0 + nq_here);
   const int kv_lo = p.window > 0 ? max(0, pos0 - p.window + 1) : 0;
-  const int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
+  int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
+  if (split_mode) {
+    // this CTA's share of the key tiles (may be empty: it then publishes an empty partial, m = -inf, l = 0)
+    const int per = (t_hi - t_lo + p.splits - 1) / p.splits;
+    t_lo = min(t_hi, t_lo + static_cast<int>(blockIdx.x) * per);
+    t_hi = min(t_hi, t_lo + per);
+  }
   const int nt = t_hi - t_lo;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -407,6 +419,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     __nv_bfloat16* dst = p.out + (static_cast<size_t>(qtok0 + i) * p.n_q + kvh * G + g) * D;
+    float* wsrow = split_mode ? p.ws + (((static_cast<size_t>(seq) * p.n_kv + kvh) * p.splits + blockIdx.x) * p.ws_rows + g) *
+                                           (D + 2) : nullptr;
+    if (split_mode && row_valid) {
+      wsrow[D] = (m_ref == -INFINITY) ? -INFINITY : m_ref * 0.6931471805599453f;     // natural-log domain for the merge pass
+      wsrow[D + 1] = l;
+    }
 #pragma unroll 1
     for (int c = 0; c < D; c += 32) {
       float o[32];
@@ -415,6 +433,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e) o[e] = 0.f;
+      }
+      if (split_mode) {
+        if (row_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(wsrow + c + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+        }
+        continue;
       }
       if (row_valid) {
 #pragma unroll
@@ -452,7 +478,8 @@ int launch_tc_cap(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     if (e != cudaSuccess) return static_cast<int>(e);
     set[dev] = true;
   }
-  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, SOFTCAP, P_TMEM>, dim3(qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
+  return static_cast<int>(launch_kernel(attn_prefill_tc_kernel<D, SOFTCAP, P_TMEM>,
+                                        dim3(p.splits > 1 ? p.splits : qblocks, p.n_kv, seqs), dim3(ATC_THREADS),
                                         Cfg::kSmemBytes, s, 1, tq, tk, tv, p, G, QB));
 }
 
@@ -482,7 +509,7 @@ bool attention_tc_supported(int n_q, int n_kv, int head_dim) {
 int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int* block_table,
                         const int* q_start, const int* q_len, const int* kv_len, int seqs, int max_q, int max_pages,
                         int n_tokens, int n_pages, int n_q, int n_kv, int head_dim, int window, float softcap,
-                        cudaStream_t s) {
+                        int splits, float* ws, cudaStream_t s) {
   if (!attention_tc_supported(n_q, n_kv, head_dim)) return -2;
   const int G = n_q / n_kv, QB = 128 / G;
   CUtensorMap tq, tk, tv;
@@ -496,13 +523,20 @@ int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache,
   p.out = static_cast<__nv_bfloat16*>(out);
   p.block_table = block_table; p.q_start = q_start; p.q_len = q_len; p.kv_len = kv_len;
   p.max_pages = max_pages; p.n_q = n_q; p.n_kv = n_kv; p.window = window; p.softcap = softcap;
+  p.splits = (max_q == 1 && splits > 1 && ws != nullptr) ? splits : 1;
+  p.ws = ws;
+  p.ws_rows = attn_rows(G, 1);
   const int qblocks = (max_q + QB - 1) / QB;
+  int rc;
   switch (head_dim) {
-    case 64: return launch_tc<64>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
-    case 128: return launch_tc<128>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
-    case 256: return launch_tc<256>(tq, tk, tv, p, G, QB, seqs, qblocks, s);
+    case 64: rc = launch_tc<64>(tq, tk, tv, p, G, QB, seqs, qblocks, s); break;
+    case 128: rc = launch_tc<128>(tq, tk, tv, p, G, QB, seqs, qblocks, s); break;
+    case 256: rc = launch_tc<256>(tq, tk, tv, p, G, QB, seqs, qblocks, s); break;
     default: return -3;
   }
+  if (rc == 0 && p.splits > 1)
+    rc = launch_attention_merge(out, q_start, ws, seqs, n_q, n_kv, head_dim, p.splits, s);
+  return rc;
 }
 
 }  // namespace b2b

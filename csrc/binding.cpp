@@ -280,6 +280,11 @@ void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, co
   // use_tc: -1 = by query-chunk length (prefill chunks), 1 = force the tcgen05 kernel (decode: one-token query blocks,
   // the GQA group stacked into the MMA rows), 0 = force the CUDA-core kernel (split-KV decode of few sequences)
   const bool want_tc = use_tc < 0 ? (max_q >= g_attn_tc_min_q && g_attn_tc_min_q > 0) : (use_tc > 0 && g_attn_tc_min_q > 0);
+  if (want_tc && splits > 1 && max_q == 1) {
+    TORCH_CHECK(ws.has_value(), "split-KV needs a workspace");
+    const int64_t R = b2b::attn_rows(static_cast<int>(n_q / n_kv), 1);
+    TORCH_CHECK(ws->numel() >= seqs * n_kv * splits * R * (head_dim + 2), "attention workspace too small");
+  }
   if (want_tc &&
       b2b::attention_tc_supported(static_cast<int>(n_q), static_cast<int>(n_kv), static_cast<int>(head_dim))) {
     // prefill chunk: tcgen05 flash attention
@@ -291,7 +296,7 @@ void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, co
                                    static_cast<int>(block_table.size(1)), static_cast<int>(q.size(0)),
                                    static_cast<int>(k_cache.size(0)), static_cast<int>(n_q), static_cast<int>(n_kv),
                                    static_cast<int>(head_dim), static_cast<int>(window), static_cast<float>(softcap),
-                                   cur_stream()),
+                                   static_cast<int>(splits), ptr_or_null<float>(ws), cur_stream()),
           "attention_tc");
     return;
   }

@@ -232,9 +232,12 @@ def test_attention_decode(hd, nq, nkv, window, softcap, use_tc):
     assert float(out[3].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("splits", [2, 5])
-def test_attention_decode_split_kv(splits):
-    hd, nq, nkv = 128, 8, 2
+@pytest.mark.parametrize("splits", [2, 5, 16])
+@pytest.mark.parametrize("use_tc", [1, 0])
+@pytest.mark.parametrize("hd,nq,nkv", [(128, 8, 2), (256, 8, 4)])
+def test_attention_decode_split_kv(splits, use_tc, hd, nq, nkv):
+    """split-KV decode: (sequence, kv head, split) CTAs + merge pass, on the tcgen05 kernel and the CUDA-core kernel;
+    splits with no tiles at all (short sequences) publish empty partials"""
     kv_lens = [1000, 130, 64, 5]
     S = len(kv_lens)
     kc, vc, bt = _paged_setup(kv_lens, nkv, hd)
@@ -244,7 +247,8 @@ def test_attention_decode_split_kv(splits):
     ar = torch.arange(S, device="cuda", dtype=torch.int32)
     ones = torch.ones(S, device="cuda", dtype=torch.int32)
     kvl = torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
-    ops.attention(q, kc, vc, out, bt, ar, ones, kvl, max_q=1, n_q=nq, n_kv=nkv, head_dim=hd, splits=splits, ws=ws)
+    ops.attention(q, kc, vc, out, bt, ar, ones, kvl, max_q=1, n_q=nq, n_kv=nkv, head_dim=hd, splits=splits, ws=ws,
+                  use_tc=use_tc)
     close(out, _attn_ref(q, kc, vc, bt, [1] * S, kv_lens, nq, nkv, hd, 0, 0.0))
 
 

@@ -29,10 +29,11 @@ for B in (32, 4):
         ref = _attn_ref(q, kc, vc, bt, [1] * B, [ctx] * B, nq, nkv, hd, 0, 0.0) if ctx <= 2048 or B <= 4 else None
         auto = max(1, min(16, 148 // (B * nkv)))
         for name, tc_min_q, splits in (("cuda-core, 1 split", 0, 1), (f"cuda-core, {max(auto, 2)} splits", 0, max(auto, 2)),
-                                       ("cuda-core, 16 splits", 0, 16), ("tcgen05 flash, 1-token blocks", 1, 1)):
-            ops.set_attn_tc_min_q(tc_min_q)
+                                       ("cuda-core, 16 splits", 0, 16), ("tcgen05 flash, 1-token blocks", 1, 1),
+                                       (f"tcgen05 flash, {max(auto, 2)} splits", 1, max(auto, 2)), ("tcgen05 flash, 16 splits", 1, 16)):
+            ops.set_attn_tc_min_q(2)
             f = lambda: ops.attention(q, kc, vc, out, bt, qs, ql, kvl, max_q=1, n_q=nq, n_kv=nkv, head_dim=hd, window=0,
-                                      softcap=0.0, splits=splits, ws=ws)
+                                      softcap=0.0, splits=splits, ws=ws, use_tc=1 if tc_min_q else 0)
             try:
                 out.zero_(); f(); torch.cuda.synchronize()
             except Exception as e:
