@@ -97,8 +97,8 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.sumsq_out = as_ptr<float>(sumsq_out);
   p.zero_buf = as_ptr<float>(zero_buf);
   p.sumsq = as_ptr<const float>(sumsq);
-  TORCH_CHECK(!p.q_out8 || (p.q_sf && p.ld_q % 128 == 0 && (epi == b2b::EPI_RESIDUAL || epi == b2b::EPI_GLU)),
-              "fused output quantisation: residual / GLU epilogues, scale-factor buffer and a row stride multiple of 128");
+  TORCH_CHECK(!p.q_out8 || (p.q_sf && p.sfa && p.ld_q % 128 == 0 && (epi == b2b::EPI_RESIDUAL || epi == b2b::EPI_GLU)),
+              "fused output quantisation: MX GEMMs with residual / GLU epilogues, scale-factor buffer, row stride multiple of 128");
   p.residual = as_ptr<const __nv_bfloat16>(residual_ptr);
   p.ld_res = static_cast<int>(ld_res);
   p.bias = ptr_or_null<const float>(bias);

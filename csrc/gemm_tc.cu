@@ -419,30 +419,53 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
     }
 
-    // fused MX quantisation of one output value per lane (32 lanes = 32 consecutive features = one block) of token `tok`
+    // Fused MX quantisation of a CHUNK of 16 tokens: every lane holds its feature's value for each token of the chunk
+    // (32 lanes = 32 consecutive features = one MX block per token).  The per-token block maximum and sum of squares are
+    // computed with a transpose-reduce (8 + 4 + 2 + 1 + 1 shuffles for all 16 tokens instead of 5 dependent shuffles per
+    // token): afterwards lanes 2t and 2t+1 hold the totals of token t.
     const int q_nkc = p.ld_q >> 7;
     const int q_chunk = p.q_bn > 128 ? 1024 : 512;
-    auto emit_q = [&](float val, int tok, int feat) {
-      const float r = bf16_round(val);                        // what a separate quantiser would read back from memory
-      float amax = fabsf(r);
+    auto emit_q_chunk = [&](const float* qv, int tok_base, int nvalid, int feat) {
+      float r[16], am[16], ss[16];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-      const uint32_t u = __float_as_uint(amax * (1.f / 448.f));
-      int e = static_cast<int>(u >> 23) - 127 + ((u & 0x7FFFFFu) ? 1 : 0);
-      e = max(-126, min(127, e));
-      const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
-      p.q_out8[static_cast<size_t>(tok) * p.ld_q + feat] =
-          static_cast<uint8_t>(__nv_cvt_float_to_fp8(r * inv, __NV_SATFINITE, __NV_E4M3));
-      float ss = r * r;
-      if (p.sumsq_out != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      for (int i = 0; i < 16; ++i) {
+        r[i] = (i < nvalid) ? bf16_round(qv[i]) : 0.f;     // what a separate quantiser would read back from memory
+        am[i] = fabsf(r[i]);
+        ss[i] = r[i] * r[i];
       }
-      if (lane == 0) {
+#pragma unroll
+      for (int s = 16, n = 8; n >= 1; s >>= 1, n >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+          const float sa = upper ? am[j] : am[j + n], ka = upper ? am[j + n] : am[j];
+          const float sq = upper ? ss[j] : ss[j + n], kq = upper ? ss[j + n] : ss[j];
+          am[j] = fmaxf(ka, __shfl_xor_sync(0xffffffffu, sa, s));
+          ss[j] = kq + __shfl_xor_sync(0xffffffffu, sq, s);
+        }
+      }
+      am[0] = fmaxf(am[0], __shfl_xor_sync(0xffffffffu, am[0], 1));
+      ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 1);
+      // this lane's token: t = (lane >> 1) & 15; e = ceil(log2(amax / 448)) clamped to the UE8M0 range
+      const uint32_t u = __float_as_uint(am[0] * (1.f / 448.f));
+      int e_mine = static_cast<int>(u >> 23) - 127 + ((u & 0x7FFFFFu) ? 1 : 0);
+      e_mine = max(-126, min(127, e_mine));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int e = __shfl_sync(0xffffffffu, e_mine, 2 * i);
+        if (i < nvalid) {
+          const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+          p.q_out8[static_cast<size_t>(tok_base + i) * p.ld_q + feat] =
+              static_cast<uint8_t>(__nv_cvt_float_to_fp8(r[i] * inv, __NV_SATFINITE, __NV_E4M3));
+        }
+      }
+      const int t = lane >> 1;
+      if ((lane & 1) == 0 && t < nvalid) {
+        const int tok = tok_base + t;
         const int tile = tok / p.q_bn, n = tok - tile * p.q_bn, rr = n & 127;
         p.q_sf[(static_cast<size_t>(tile) * q_nkc + (feat >> 7)) * q_chunk + (n >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4 +
-               ((feat >> 5) & 3)] = static_cast<uint8_t>(e + 127);
-        if (p.sumsq_out != nullptr) atomicAdd(&p.sumsq_out[tok], ss);
+               ((feat >> 5) & 3)] = static_cast<uint8_t>(e_mine + 127);
+        if (p.sumsq_out != nullptr) atomicAdd(&p.sumsq_out[tok], ss[0]);
       }
     };
 
@@ -505,6 +528,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
       float v[16];
       load_acc(c, n, v);
+      float qv[16];                              // outputs of this chunk for the fused quantiser
+      int q_valid = 0;
 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -525,14 +550,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
           if (p.out2 != nullptr)
             reinterpret_cast<__nv_bfloat16*>(p.out2)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
-          if (p.q_out8 != nullptr) emit_q(rv, tok, n_glob);
+          qv[i] = rv;
+          q_valid = i + 1;
         } else if constexpr (EPI == EPI_GLU) {
           const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
           if (p.out != nullptr)
             reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
                 __float2bfloat16_rn(g * u);
-          if (p.q_out8 != nullptr) emit_q(g * u, tok, tile_n * 64 + row);
+          qv[i] = g * u;
+          q_valid = i + 1;
         } else {   // EPI_QKV_ROPE
           float o = a;
           if (sect < 2 && p.rope_theta > 0.f) {
@@ -550,6 +577,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             if (slot >= 0) dst[static_cast<size_t>(slot) * kv_dim + f_in_sect] = __float2bfloat16_rn(o);
           }
         }
+      }
+      if constexpr (MX && (EPI == EPI_RESIDUAL || EPI == EPI_GLU)) {     // (only the MX instantiations pay the registers)
+        if (p.q_out8 != nullptr)        // warp-uniform: the valid tokens of a chunk are a prefix
+          emit_q_chunk(qv, tok0 + col0 + c, q_valid, EPI == EPI_GLU ? tile_n * 64 + row : n_glob);
       }
     }
 
