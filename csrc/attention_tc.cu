@@ -200,6 +200,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int per = (t_hi - t_lo + p.splits - 1) / p.splits;
     t_lo = min(t_hi, t_lo + static_cast<int>(blockIdx.x) * per);
     t_hi = min(t_hi, t_lo + per);
+    if (t_hi <= t_lo) {
+      // empty share (short sequence, many splits): publish an empty partial and leave before any TMA / TMEM / barrier
+      // state exists (a CTA must not exit with a Q load in flight)
+      if (threadIdx.x < G) {
+        float* w = p.ws + (((static_cast<size_t>(seq) * p.n_kv + kvh) * p.splits + blockIdx.x) * p.ws_rows + threadIdx.x) * (D + 2);
+        for (int c = 0; c < D; ++c) w[c] = 0.f;
+        w[D] = -INFINITY;
+        w[D + 1] = 0.f;
+      }
+      return;
+    }
   }
   const int nt = t_hi - t_lo;
 
