@@ -154,12 +154,19 @@ class Engine:
     def __init__(self, model: str = "tiny-llama", cfg: Optional[ModelConfig] = None, device: Optional[str] = None,
                  pieces: int = 1, max_batch: int = 8, max_seq_len: int = 2048, max_prefill_tokens: int = 2048,
                  decode_burst: int = 8, seed: int = 0, runner=None, groups: int = 1, rank: int = 0, world: int = 1,
-                 control_group=None, plan_sync: bool = False, plan_group=None, quant: str = "bf16"):
+                 control_group=None, plan_sync: bool = False, plan_group=None, quant: str = "bf16",
+                 overlap_prefill: bool = True):
         self.model = model
         # plan_sync: rank 0 owns the request queue and broadcasts every newly arrived request to the
         # follower ranks at the top of each step (serving); False = every rank is fed identical
         # requests by its caller (SPMD benchmark / tests)
         self.plan_sync, self.plan_group = plan_sync, plan_group
+        # overlap_prefill: when none of the newly admitted requests streams tokens to a callback, the decode burst is
+        # enqueued right behind the prefill and the first tokens are read together with the burst's (one read-back, no
+        # pipeline drain between prefill and decode: piece 0's embed kernel waits per group for the prefill chunks that
+        # hold its sequences).  Streaming requests keep the early first-token read-back (TTFT).
+        self.overlap_prefill = overlap_prefill
+        self._first_pending = False
         self.cfg = cfg or resolve_config(model)
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
@@ -411,19 +418,25 @@ class Engine:
             for r in admitted:
                 self.stats["prefill_tokens"] += len(r.prompt_ids)
                 self.stats["requests"] += 1
-            self._collect(first=True)
+            if self.overlap_prefill and not any(r.on_token is not None for r in admitted):
+                self._first_pending = True
+            else:
+                self._collect(first=True)
         if not self._running:
             if admitted:
                 self.stats["busy_s"] += time.time() - t0
             return bool(admitted) or bool(cancelled)
-        remaining = min(r.params.max_new_tokens - len(r.out_ids) for r in self._running.values())
+        # a request whose first token (sampled by the prefill) has not been collected yet still owes one token less
+        remaining = min(r.params.max_new_tokens - len(r.out_ids) - (1 if r.consumed == 0 else 0)
+                        for r in self._running.values())
         n = max(1, min(self.decode_burst, remaining, getattr(self.runner, "hist_len", 1 << 30)))
         th = time.perf_counter()
         self.runner.decode(n)
         tc = time.perf_counter()
         self.host_ms["decode"] += (tc - th) * 1e3
         self.stats["steps"] += n
-        self._collect(steps=n)          # blocks on the device-side "burst complete on every rank" condition
+        self._collect(steps=n, include_first=self._first_pending)   # blocks on the device-side "burst complete on every rank" condition
+        self._first_pending = False
         self.host_ms["collect"] += (time.perf_counter() - tc) * 1e3
         self.stats["busy_s"] += time.time() - t0
         return True
@@ -465,9 +478,11 @@ class Engine:
         self.d2h_bytes += win.numel() * 4
         return win
 
-    def _collect(self, first: bool = False, steps: int = 0) -> None:
-        """Pull freshly produced tokens for every running request, stream them, retire finished ones."""
-        width = 1 if first else steps
+    def _collect(self, first: bool = False, steps: int = 0, include_first: bool = False) -> None:
+        """Pull freshly produced tokens for every running request, stream them, retire finished ones.
+        ``include_first``: requests admitted by the last prefill have not had their first token read yet -- their window
+        is one token longer (first token + the burst)."""
+        width = 1 if first else steps + (1 if include_first else 0)
         if self.gpu:
             win = self._fetch_window(width, first=first)
         finished: List[int] = []
@@ -476,7 +491,7 @@ class Engine:
         if self.gpu:
             win = win.numpy()
         for b, r in list(self._running.items()):
-            have = 1 if first and r.consumed == 0 else steps
+            have = 1 if first and r.consumed == 0 else steps + (1 if (include_first and r.consumed == 0) else 0)
             if first and r.consumed > 0:
                 continue
             row = win[b, :have] if self.gpu else np.asarray(self.runner.tokens_of(b, r.consumed, have), dtype=np.int64)

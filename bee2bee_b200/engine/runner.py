@@ -30,7 +30,7 @@ from .. import ops
 from ..models.config import UNITS_PER_LAYER, ModelConfig, piece_units, unit_layers
 from ..models.native import BatchMeta, NativePiece
 from ..models.weights import load_or_init
-from ..parallel.mesh import F_TOK_DONE, M_PF_SEEN, MeshComm
+from ..parallel.mesh import F_TOK_DONE, MeshComm
 from .kv import PAGE
 
 
@@ -151,7 +151,8 @@ class GpuRunner:
             self.decode_splits = max(1, min(self.piece.max_splits, ops.NUM_SMS // max(1, self.gb * cfg.n_kv_heads)))
         # ---- host <-> device rendezvous without collectives
         self.tok_target = [1] * groups              # value rank 0's token flag of group g reaches after the enqueued steps
-        self.pf_calls = 0                           # prefill() calls so far == target of the prefill-done counter
+        self.pf_calls = 0                           # prefill() calls so far
+        self.pf_need = [0] * groups                 # chunks the last piece must have completed before group g may decode
         self.pf_chunks = 0                          # chunks sent through the prefill channel (parity of the staging buffer)
         self._cur = _HostRing(self.C, B)            # per-slot read cursors (host writes, kernel reads)
         self._waits = _HostRing(self.C, 4 * (groups + 2))
@@ -210,15 +211,18 @@ class GpuRunner:
             self._install(seqs)
             for chunk in self._pack(seqs):
                 self._run_chunk(chunk)
+                # the last piece publishes "chunk #n done: its sequences' first tokens are in rank 0's ring" (inside the
+                # chunk graph); a group may start decoding as soon as the chunks holding ITS sequences are through --
+                # piece 0's embed kernel waits for that count, so decode can be enqueued right behind the prefill and
+                # the pipeline never drains between the two
+                for s, _, c1 in chunk:
+                    if c1 == len(s.prompt):
+                        g = s.slot // self.gb
+                        self.pf_need[g] = max(self.pf_need[g], self.pf_chunks)
             self.pf_calls += 1
-            if self.world > 1:
-                if self.last:
-                    flag, epoch = self.mesh.pf_done_signal()
-                    self.C.flag_signal(flag, epoch, 0, 0)       # "first tokens of prefill #n are in rank 0's ring"
-                if self.first:
-                    # rank 0's next decode step embeds those tokens: order its stream behind the publication
-                    zero = self.mesh._flag(self.mesh.local, self.mesh.misc_channel, M_PF_SEEN)
-                    self.C.flag_wait(self.mesh.pf_done_flag(), zero, self.pf_calls)
+            if self.world > 1 and self.first:
+                need = torch.tensor(self.pf_need, dtype=torch.int32).pin_memory()
+                self.mesh.local_view("pf_need", (self.groups,), "i32").copy_(need, non_blocking=True)
 
     def _install(self, seqs: Sequence[SeqInit]) -> None:
         """Per-sequence state of all admitted sequences in a handful of batched copies (one tiny launch per field
@@ -325,6 +329,9 @@ class GpuRunner:
                            history=self.mesh.hist_base() if multi else self.history.data_ptr(), hist_pos=self.hist_pos,
                            hist_stride=self.hist_len, peer_tokens=self.mesh.tok_base() if multi else 0,
                            row_map=v["row_map"].data_ptr())
+                if multi:
+                    flag, epoch = self.mesh.pf_done_signal()
+                    self.C.flag_signal(flag, epoch, 0, 0)       # chunk counter on rank 0 (release after the peer stores)
             self.C.set_decode_state(self.positions, self.kv_len, self.q_len, v["row_map"].data_ptr(),
                                     v["kv_len"].data_ptr(), sb)
 
@@ -513,8 +520,8 @@ class GpuRunner:
             for g in range(self.groups):
                 w64[2 * n_waits], w64[2 * n_waits + 1] = self.mesh.tok_flag(g), self.tok_target[g]
                 n_waits += 1
-            if first or self.pf_calls:
-                w64[2 * n_waits], w64[2 * n_waits + 1] = self.mesh.pf_done_flag(), self.pf_calls
+            if first or self.pf_chunks:
+                w64[2 * n_waits], w64[2 * n_waits + 1] = self.mesh.pf_done_flag(), self.pf_chunks
                 n_waits += 1
         hist = self.mesh.hist_base() if self.world > 1 else self.history.data_ptr()
         with torch.cuda.stream(self.stream):

@@ -49,6 +49,8 @@ class Handoff:
     out_free: int = 0        # u32: downstream acks land here (local)
     done: int = 0            # u32 scratch counter (local)
     free_lag: int = 0        # payloads that may be outstanding on the output slot (1 = double-buffered staging)
+    pf_flag: int = 0         # piece 0, decode: counter of prefill chunks completed by the last piece (local)
+    pf_need: int = 0         # piece 0, decode: u32 word = chunks that must be complete before this group may embed
 
 
 @dataclass
@@ -285,7 +287,8 @@ class NativePiece:
             ops.embed(m.ids, self.w["embed"], x, pos_table=self.w.get("pos_embed"),
                       positions=m.positions if c.rope_theta <= 0 else None,
                       scale=float(torch.tensor(c.embed_scale, dtype=torch.bfloat16)) if c.embed_scale != 1.0 else 1.0,
-                      tok_flag=hand.in_flag, tok_epoch=hand.in_epoch if hand.in_flag else 0)
+                      tok_flag=hand.in_flag, tok_epoch=hand.in_epoch if hand.in_flag else 0,
+                      pf_flag=hand.pf_flag if hand.in_flag else 0, pf_need=hand.pf_need if hand.in_flag else 0)
             wait_flag = wait_epoch = 0
         else:
             x = x_in[:T]

@@ -314,9 +314,9 @@ def layernorm(x, gamma, beta, out=None, eps=1e-5):
     return out
 
 
-def embed(ids, table, out, pos_table=None, positions=None, scale=1.0, tok_flag=0, tok_epoch=0):
+def embed(ids, table, out, pos_table=None, positions=None, scale=1.0, tok_flag=0, tok_epoch=0, pf_flag=0, pf_need=0):
     native().embed(ids.data_ptr() if isinstance(ids, torch.Tensor) else int(ids), table, pos_table, positions, out,
-                   scale, tok_flag, tok_epoch)
+                   scale, tok_flag, tok_epoch, pf_flag, pf_need)
     return out
 
 

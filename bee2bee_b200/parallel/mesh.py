@@ -27,6 +27,7 @@ FLAG_WORDS = 16          # u32 slots per channel (64 B, one line per channel)
 F_IN_FLAG, F_IN_EPOCH, F_OUT_EPOCH, F_OUT_FREE, F_DONE, F_TOK_DONE = 0, 1, 2, 3, 4, 5
 # misc channel (index groups + 1): prefill completion, published by the last rank on rank 0
 M_PF_FLAG, M_PF_EPOCH, M_PF_SEEN = 0, 1, 2
+M_PF_NEED0 = 4           # misc words 4.. : per micro-batch group, chunks that must be complete before the group may decode (<= 12 groups per line; more groups spill into a dedicated buffer)
 
 
 @dataclass
@@ -68,6 +69,7 @@ class MeshComm:
             "stage_h": self.groups * self.group_batch * self.ffn * 2,           # MLP hidden of a gate/up | down cut
             "stage_h_pf": 2 * self.max_tokens * self.ffn * 2,
             "flags": (self.groups + 2) * FLAG_WORDS * 4,                        # groups, prefill channel, misc
+            "pf_need": max(64, self.groups * 4),                                # rank 0: chunks each group waits for
             "tok": self.groups * self.group_batch * 4,                          # sampled-token return buffer (rank 0)
             "hist": self.groups * self.group_batch * self.hist_len * 4,         # token history ring (rank 0)
         }
@@ -131,6 +133,9 @@ class MeshComm:
         h.out_epoch = self._flag(self.local, group, F_OUT_EPOCH)
         h.done = self._flag(self.local, group, F_DONE)
         h.in_x = (self.local["tok"] + tok_off) if first else (self.local["stage"] + stage_off)
+        if first:
+            h.pf_flag = self._flag(self.local, self.misc_channel, M_PF_FLAG)
+            h.pf_need = self.local["pf_need"] + group * 4
         h_off = group * self.group_batch * self.ffn * 2
         if self.ffn and not first:
             h.in_h = self.local["stage_h"] + h_off

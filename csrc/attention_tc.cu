@@ -448,8 +448,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (split_mode) {
         if (row_valid) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(wsrow + c + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+          for (int e = 0; e < 32; e += 2)      // rows are (D + 2) floats apart: 8-byte, not 16-byte, aligned
+            *reinterpret_cast<float2*>(wsrow + c + e) = make_float2(o[e], o[e + 1]);
         }
         continue;
       }

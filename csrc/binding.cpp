@@ -182,14 +182,15 @@ void layernorm(const Tensor& x, const Tensor& gamma, const Tensor& beta, const T
 }
 
 void embed(int64_t ids_ptr, const Tensor& table, const OptT& pos_table, const OptT& positions, const Tensor& out,
-           double scale, int64_t tok_flag, int64_t tok_epoch) {
+           double scale, int64_t tok_flag, int64_t tok_epoch, int64_t pf_flag, int64_t pf_need) {
   check_bf16(table, "table");
   c10::cuda::CUDAGuard guard(table.device());
   const int h = static_cast<int>(table.size(1));
   check(b2b::launch_embed(as_ptr<const int>(ids_ptr), table.data_ptr(), ptr_or_null<void>(pos_table),
                           ptr_or_null<const int>(positions), out.data_ptr(), static_cast<int>(out.numel() / h), h,
                           static_cast<int>(table.size(0)), static_cast<float>(scale), as_ptr<const uint32_t>(tok_flag),
-                          as_ptr<const uint32_t>(tok_epoch), cur_stream()),
+                          as_ptr<const uint32_t>(tok_epoch), as_ptr<const uint32_t>(pf_flag), as_ptr<const uint32_t>(pf_need),
+                          cur_stream()),
         "embed");
 }
 

@@ -103,11 +103,17 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 __global__ void embed_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                              const __nv_bfloat16* __restrict__ pos_table, const int* __restrict__ positions,
                              __nv_bfloat16* __restrict__ out, int h, int vocab, float scale,
-                             const uint32_t* tok_flag, const uint32_t* tok_epoch) {
+                             const uint32_t* tok_flag, const uint32_t* tok_epoch, const uint32_t* pf_flag,
+                             const uint32_t* pf_need) {
   pdl_launch_dependents();
   pdl_wait();
   if (tok_flag != nullptr) {
-    if (threadIdx.x == 0) wait_flag_ge(tok_flag, *reinterpret_cast<const volatile uint32_t*>(tok_epoch) + 1);
+    if (threadIdx.x == 0) {
+      wait_flag_ge(tok_flag, *reinterpret_cast<const volatile uint32_t*>(tok_epoch) + 1);
+      // decode may be enqueued right behind a prefill: the first tokens of this group's new sequences are published
+      // by the last piece chunk by chunk (pf_flag counts chunks); *pf_need = chunks that must have completed
+      if (pf_flag != nullptr) wait_flag_ge(pf_flag, *reinterpret_cast<const volatile uint32_t*>(pf_need));
+    }
     __syncthreads();
   }
   const int t = blockIdx.x;
@@ -401,11 +407,12 @@ int launch_layernorm(const void* x, const void* gamma, const void* beta, void* o
   return static_cast<int>(cudaGetLastError());
 }
 int launch_embed(const int* ids, const void* table, const void* pos_table, const int* positions, void* out, int tokens,
-                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, cudaStream_t s) {
+                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, const uint32_t* pf_flag,
+                 const uint32_t* pf_need, cudaStream_t s) {
   if (h % 8) return -2;
   launch_kernel(embed_kernel, dim3(tokens), dim3(256), 0, s, 1, ids, static_cast<const __nv_bfloat16*>(table),
                                       static_cast<const __nv_bfloat16*>(pos_table), positions,
-                                      static_cast<__nv_bfloat16*>(out), h, vocab, scale, tok_flag, tok_epoch);
+                                      static_cast<__nv_bfloat16*>(out), h, vocab, scale, tok_flag, tok_epoch, pf_flag, pf_need);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int* slots, int tokens,

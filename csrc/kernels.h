@@ -13,7 +13,8 @@ int launch_rmsnorm(const void* x, const void* gamma, const void* residual, void*
 int launch_layernorm(const void* x, const void* gamma, const void* beta, void* out, int tokens, int h, float eps,
                      cudaStream_t s);
 int launch_embed(const int* ids, const void* table, const void* pos_table, const int* positions, void* out, int tokens,
-                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, cudaStream_t s);
+                 int h, int vocab, float scale, const uint32_t* tok_flag, const uint32_t* tok_epoch, const uint32_t* pf_flag,
+                 const uint32_t* pf_need, cudaStream_t s);
 int launch_kv_append(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int* slots, int tokens,
                      int q_dim, int kv_dim, float q_scale, cudaStream_t s);
 int launch_add(const void* a, const void* b, void* out, size_t n, cudaStream_t s);
