@@ -155,7 +155,7 @@ class Engine:
                  pieces: int = 1, max_batch: int = 8, max_seq_len: int = 2048, max_prefill_tokens: int = 2048,
                  decode_burst: int = 8, seed: int = 0, runner=None, groups: int = 1, rank: int = 0, world: int = 1,
                  control_group=None, plan_sync: bool = False, plan_group=None, quant: str = "bf16",
-                 overlap_prefill: bool = True):
+                 overlap_prefill: bool = True, prefix_cache: bool = True):
         self.model = model
         # plan_sync: rank 0 owns the request queue and broadcasts every newly arrived request to the
         # follower ranks at the top of each step (serving); False = every rank is fed identical
@@ -191,7 +191,10 @@ class Engine:
             self.runner = TorchRunner(self.cfg, model, pieces=pieces, device=self.device, max_batch=max_batch, seed=seed)
         self.gpu = self.device.type == "cuda"
         pages_per_seq = (max_seq_len + PAGE - 1) // PAGE
-        self.alloc = PageAllocator(getattr(self.runner, "num_pages", 1 + max_batch * pages_per_seq))
+        # prefix cache: only the paged GPU backend can share KV pages between sequences (the CPU oracle keeps a dense
+        # cache per slot)
+        self.alloc = PageAllocator(getattr(self.runner, "num_pages", 1 + max_batch * pages_per_seq),
+                                   prefix_cache=self.gpu and prefix_cache)
         self._ids = itertools.count(1)
         self._waiting: "queue.Queue[Request]" = queue.Queue()
         self._pending: List[Request] = []
@@ -283,7 +286,8 @@ class Engine:
                 "prefill_tokens": self.stats["prefill_tokens"], "decode_steps": self.stats["steps"],
                 "tokens_per_s": self.stats["tokens"] / busy, "running": len(self._running),
                 "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
-                "healthy": self.broken is None, "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
+                "healthy": self.broken is None, "prefix_cache": self.alloc.cache_stats(),
+                "prefix_cache_hit_tokens": self.stats.get("prefix_cache_hit_tokens", 0), "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
                 "d2h_bytes": self.d2h_bytes, "native_launches": getattr(self.runner, "kernel_launches", 0),
                 "host_ms": dict(self.host_ms),
                 "ttft_ms": ({"count": len(self._ttfts), "p50": statistics.median(self._ttfts),
@@ -353,6 +357,7 @@ class Engine:
         except Exception:
             pass
         for b in self._running:
+            self.alloc.invalidate(b)            # a failed burst may have left half-written KV pages behind
             self.alloc.release(b)
             self._free_slots.append(b)
         self._running.clear()
@@ -388,9 +393,9 @@ class Engine:
         still: List[Request] = []
         for r in self._pending:
             need = len(r.prompt_ids) + r.params.max_new_tokens
-            if self._free_slots and self.alloc.can_allocate(need):
+            if self._free_slots and self.alloc.can_allocate(need, r.prompt_ids):
                 r.slot = self._free_slots.pop()
-                self.alloc.allocate(r.slot, need)
+                self.alloc.allocate(r.slot, need, r.prompt_ids)
                 admitted.append(r)
             else:
                 still.append(r)
@@ -399,8 +404,11 @@ class Engine:
             seqs = [SeqInit(slot=r.slot, prompt=r.prompt_ids, pages=self.alloc.owned(r.slot),
                             temperature=r.params.temperature, top_p=r.params.top_p,
                             repetition_penalty=r.params.repetition_penalty,
-                            seed=r.params.seed if r.params.seed is not None else (r.rid * 2654435761) & 0x7FFFFFFF)
+                            seed=r.params.seed if r.params.seed is not None else (r.rid * 2654435761) & 0x7FFFFFFF,
+                            cached=self.alloc.cached_tokens(r.slot))
                     for r in admitted]
+            for r in admitted:          # after the whole admission round: requests of one round never share with each other
+                self.alloc.commit(r.slot, r.prompt_ids)
             from ..utils.tracing import TRACER
             th = time.perf_counter()
             # the admitted requests are "running" from here on, so that a failing prefill is cleaned up by
@@ -416,7 +424,8 @@ class Engine:
                 raise
             self.host_ms["prefill"] += (time.perf_counter() - th) * 1e3
             for r in admitted:
-                self.stats["prefill_tokens"] += len(r.prompt_ids)
+                self.stats["prefill_tokens"] += len(r.prompt_ids) - self.alloc.cached_tokens(r.slot)
+                self.stats["prefix_cache_hit_tokens"] = self.stats.get("prefix_cache_hit_tokens", 0) + self.alloc.cached_tokens(r.slot)
                 self.stats["requests"] += 1
             if self.overlap_prefill and not any(r.on_token is not None for r in admitted):
                 self._first_pending = True

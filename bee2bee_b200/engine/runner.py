@@ -44,6 +44,7 @@ class SeqInit:
     top_p: float = 0.95
     repetition_penalty: float = 1.15
     seed: int = 0
+    cached: int = 0          # leading prompt tokens whose KV is already resident in ``pages`` (prefix cache): not prefilled
 
 
 def _pow2_at_least(n: int, lo: int = 1) -> int:
@@ -259,7 +260,7 @@ class GpuRunner:
         work: List[Tuple[SeqInit, int, int]] = []
         for s in seqs:
             L = len(s.prompt)
-            for c0 in range(0, L, self.max_prefill_tokens):
+            for c0 in range(min(s.cached, L - 1), L, self.max_prefill_tokens):     # the cached prefix is attended to, not recomputed
                 work.append((s, c0, min(L, c0 + self.max_prefill_tokens)))
         batch: List[Tuple[SeqInit, int, int]] = []
         used = 0

@@ -350,3 +350,43 @@ def test_engine_marks_itself_broken_when_the_mesh_stalls():
     assert not eng._running and eng.alloc.free_pages == eng.alloc.num_pages - 1
     eng.stop()
     eng.runner.decode = real
+
+
+def test_prefix_cache_allocator_shares_pins_and_evicts():
+    """content-addressed prompt pages: share (ref-counted), keep after release (LRU), evict under pressure"""
+    from bee2bee_b200.engine.kv import OutOfPages, PageAllocator
+
+    a = PageAllocator(10)                                   # 9 usable pages
+    p1 = list(range(200))
+    pages1 = a.allocate(1, 260, p1)
+    assert len(pages1) == 5 and a.cached_tokens(1) == 0
+    a.commit(1, p1)                                         # 3 full prompt pages become shareable
+    pages2 = a.allocate(2, 260, p1[:150] + [9, 9, 9])       # shares the first 2 pages (128 tokens), 3 fresh ones
+    assert pages2[:2] == pages1[:2] and a.cached_tokens(2) == 128 and a.free_pages == 1
+    assert not a.can_allocate(3 * 64)
+    a.release(1)                                            # shared pages stay pinned by owner 2; page 3 stays cached
+    assert a.free_pages == 4 and a.cache_stats()["evictable_pages"] == 1
+    a.release(2)
+    assert a.free_pages == 9
+    pages3 = a.allocate(3, 200, p1)                         # whole prompt minus its last token is resident: 3 pages
+    assert pages3[:3] == pages1[:3] and a.cached_tokens(3) == 192
+    a.release(3)
+    big = a.allocate(4, 9 * 64)                             # pressure: every cached page is evicted
+    assert len(big) == 9 and a.cache_stats()["cached_pages"] == 0
+    with pytest.raises(OutOfPages):
+        a.allocate(5, 64)
+    # a prompt that fits exactly into full pages still prefills its last token
+    b = PageAllocator(10)
+    q = list(range(128))
+    b.allocate(1, 192, q); b.commit(1, q); b.release(1)
+    b.allocate(2, 192, q)
+    assert b.cached_tokens(2) == 64
+    # invalidate: pages of a failed prefill lose their keys
+    c = PageAllocator(10)
+    c.allocate(1, 192, q); c.commit(1, q); c.invalidate(1); c.release(1)
+    c.allocate(2, 192, q)
+    assert c.cached_tokens(2) == 0
+    # the CPU backend (dense per-slot KV) never shares
+    d = PageAllocator(10, prefix_cache=False)
+    d.allocate(1, 192, q); d.commit(1, q); d.release(1); d.allocate(2, 192, q)
+    assert d.cached_tokens(2) == 0

@@ -200,3 +200,29 @@ def test_legacy_worker_hf_part_on_the_gpu_data_plane():
     r3 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": a["model_id"], "ids": [int(want.argmax())], "keep_on_device": True})
     r4 = ex.execute({"kind": P.HF_PART_FORWARD, "model_id": b["model_id"], "hidden_ref": r3["hidden_ref"]})
     assert len(r4["hidden"][0][0]) == cfg.vocab_size
+
+
+def test_prefix_cache_shares_kv_pages_and_skips_prefill():
+    """Round 2: content-addressed prompt pages.  A second request with the same 150-token prefix re-uses the resident KV
+    pages (same physical pages in its block table) and prefills only its suffix; greedy output equals the engine without
+    the cache.  The reference re-sends and re-computes the whole transcript every turn."""
+    V = resolve_config("tiny-llama").vocab_size
+    sys_prompt = [(11 * i + 3) % (V - 8) + 4 for i in range(150)]
+    prompts = [sys_prompt + [5, 6, 7], sys_prompt + [9, 10, 11, 12], sys_prompt[:70] + [1, 2]]
+    sp = SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True)
+    outs, stats = [], []
+    for cache in (True, False):
+        eng = Engine("tiny-llama", device="cuda:0", max_batch=4, max_seq_len=512, max_prefill_tokens=128, decode_burst=3,
+                     prefix_cache=cache)
+        res = [eng.generate([p], sp)[0] for p in prompts]            # one after the other: later ones can hit the cache
+        res.append(eng.generate(prompts, sp))                         # and all at once (requests of one round do not share)
+        outs.append(res)
+        stats.append(eng.metrics())
+        eng.close()
+    assert outs[0] == outs[1]
+    on, off = stats
+    assert off["prefix_cache_hit_tokens"] == 0
+    # second prompt: 2 full pages (128 tokens) of the shared prefix; third: 1 page; the batch round: 2 + 2 + 1 pages
+    assert on["prefix_cache_hit_tokens"] == 128 + 64 + (128 + 128 + 64)
+    assert on["prefill_tokens"] == off["prefill_tokens"] - on["prefix_cache_hit_tokens"]
+    assert on["prefix_cache"]["cached_pages"] >= 2
