@@ -348,9 +348,13 @@ class NativePiece:
                 ops.kv_append(self.qkv_buf[:T], self.q_buf, self.k_cache[l], self.v_cache[l], m.slots, c.q_dim,
                               c.kv_dim, c.softmax_scale)
             if do_attn:
+                # mxfp8: the attention kernel emits the e4m3 copy of its output for the O-proj itself (no quantiser launch)
+                a_fused = fuse and not c.post_norms and ops.attention_fuses_quant(m.max_q, c.n_heads, c.n_kv_heads, c.head_dim,
+                                                                                 m.splits)
+                aq_kw = dict(fq_out=self._qbuf[c.q_dim][:T], fq_sf=self._qsf[c.q_dim], fq_bn=q_bn) if a_fused else {}
                 ops.attention(self.q_buf, self.k_cache[l], self.v_cache[l], self.attn_buf, m.block_table, m.q_start,
                               m.q_len, m.kv_len, max_q=m.max_q, n_q=c.n_heads, n_kv=c.n_kv_heads, head_dim=c.head_dim,
-                              window=c.layer_window(l), softcap=c.attn_softcap, splits=m.splits, ws=self.attn_ws)
+                              window=c.layer_window(l), softcap=c.attn_softcap, splits=m.splits, ws=self.attn_ws, **aq_kw)
                 a = self.attn_buf[:T]
                 okw = {} if do_mlp else tail_kw          # piece ends after this attention block: O-proj is the tail GEMM
                 o_out = None if okw else x2
@@ -365,7 +369,10 @@ class NativePiece:
                     o = ops.gemm(self.w[p + "wo"], a, out=self.n_buf[:T], epi=ops.EPI_PLAIN)
                     ops.rmsnorm(o, self.w[p + "post_attn_w"], out=x2, residual=x, eps=eps, plus_one=c.gemma_norm)
                 elif self.fp8:
-                    aq, akw = self._quant(a, with_rms=False)
+                    if a_fused:
+                        aq, akw = self._qbuf[c.q_dim][:T], dict(sfb=self._qsf[c.q_dim])
+                    else:
+                        aq, akw = self._quant(a, with_rms=False)
                     x2_fused = fuse and do_gu and do_down          # this layer's gate/up and down run here
                     fq = {}
                     if fuse:

@@ -333,7 +333,7 @@ def add(a, b, out=None):
 
 # -------------------------------------------------------------------- attention
 def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, max_q, n_q, n_kv, head_dim,
-              window=0, softcap=0.0, splits=1, ws=None, use_tc=-1):
+              window=0, softcap=0.0, splits=1, ws=None, use_tc=-1, fq_out=None, fq_sf=None, fq_bn=0):
     """Paged-KV attention.  Prefill chunks (max_q >= 2) run on the tcgen05 flash kernel.  Decode (max_q == 1) also does
     when the batch fills the machine (sequences x kv heads >= 128 CTAs) or no split-KV was asked for: measured on B200
     (profiles/decode_attention.md) it streams the KV pages at 0.66 of the HBM peak at 8k context against 0.49 for the
@@ -344,8 +344,17 @@ def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, 
         # streams its share of the pages, the shared merge pass combines the partials
         use_tc = 1
     native().attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, ws, max_q, n_q, n_kv, head_dim,
-                       window, softcap, splits, use_tc)
+                       window, softcap, splits, use_tc, _ptr(fq_out), _ptr(fq_sf), fq_bn)
     return out
+
+
+def attention_fuses_quant(max_q: int, n_q: int, n_kv: int, head_dim: int, splits: int) -> bool:
+    """True when ``attention`` will run the tcgen05 kernel without split-KV, i.e. can emit the e4m3 copy itself."""
+    g = n_q // max(1, n_kv)
+    tc_ok = n_kv > 0 and n_q % n_kv == 0 and g in (1, 2, 4, 8, 16) and head_dim in (64, 128, 256) and get_attn_tc_min_q() > 0
+    if not tc_ok:
+        return False
+    return (max_q == 1 and splits <= 1) or (max_q > 1 and max_q >= get_attn_tc_min_q())
 
 
 def set_attn_tc_min_q(n: int) -> None:

@@ -16,6 +16,7 @@
 #include "kernels.h"
 
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include <cstdlib>
 #include <type_traits>
@@ -47,6 +48,12 @@ struct AttnTcParams {
   // ws[((seq * n_kv + kvh) * splits + split) * ws_rows + head_in_group][D + 2]
   int splits, ws_rows;
   float* ws;
+  // fused MX quantisation of the output for the O-proj GEMM (mxfp8 pieces): every thread owns whole 32-feature blocks of
+  // its (token, head) row, so the block maximum is a register reduction: e4m3 bytes + UE8M0 scale in the consumer's
+  // tcgen05.cp chunk layout (token tile q_bn).  Not available in split-KV mode (the merge pass writes the output).
+  uint8_t* q_out8;
+  uint8_t* q_sf;
+  int q_bn;
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -453,7 +460,35 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         continue;
       }
-      if (row_valid) {
+      if (row_valid && p.q_out8 != nullptr) {
+        // e4m3 + block scale of these 32 features (what a separate quantiser would compute from the bf16 output)
+        float amax = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          o[e] = __bfloat162float(__float2bfloat16_rn(o[e] * inv));
+          amax = fmaxf(amax, fabsf(o[e]));
+        }
+        const uint32_t u = __float_as_uint(amax * (1.f / 448.f));
+        int ex = static_cast<int>(u >> 23) - 127 + ((u & 0x7FFFFFu) ? 1 : 0);
+        ex = max(-126, min(127, ex));
+        const float sc = __uint_as_float(static_cast<uint32_t>(127 - ex) << 23);
+        const int tok = qtok0 + i, feat = (kvh * G + g) * D + c, ldq = p.n_q * D;
+        uint32_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t b = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            b |= static_cast<uint32_t>(__nv_cvt_float_to_fp8(o[4 * j + e] * sc, __NV_SATFINITE, __NV_E4M3)) << (8 * e);
+          w8[j] = b;
+        }
+        uint4* q4 = reinterpret_cast<uint4*>(p.q_out8 + static_cast<size_t>(tok) * ldq + feat);
+        q4[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+        q4[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+        const int tile = tok / p.q_bn, n = tok - tile * p.q_bn, rr = n & 127;
+        p.q_sf[(static_cast<size_t>(tile) * (ldq >> 7) + (feat >> 7)) * (p.q_bn > 128 ? 1024 : 512) + (n >> 7) * 512 +
+               (rr & 31) * 16 + (rr >> 5) * 4 + ((feat >> 5) & 3)] = static_cast<uint8_t>(ex + 127);
+      } else if (row_valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t w[4];
@@ -520,7 +555,7 @@ bool attention_tc_supported(int n_q, int n_kv, int head_dim) {
 int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int* block_table,
                         const int* q_start, const int* q_len, const int* kv_len, int seqs, int max_q, int max_pages,
                         int n_tokens, int n_pages, int n_q, int n_kv, int head_dim, int window, float softcap,
-                        int splits, float* ws, cudaStream_t s) {
+                        int splits, float* ws, void* q_out8, void* q_sf, int q_bn, cudaStream_t s) {
   if (!attention_tc_supported(n_q, n_kv, head_dim)) return -2;
   const int G = n_q / n_kv, QB = 128 / G;
   CUtensorMap tq, tk, tv;
@@ -537,6 +572,10 @@ int launch_attention_tc(const void* q, const void* k_cache, const void* v_cache,
   p.splits = (max_q == 1 && splits > 1 && ws != nullptr) ? splits : 1;
   p.ws = ws;
   p.ws_rows = attn_rows(G, 1);
+  p.q_out8 = p.splits > 1 ? nullptr : static_cast<uint8_t*>(q_out8);
+  p.q_sf = static_cast<uint8_t*>(q_sf);
+  p.q_bn = q_bn > 0 ? q_bn : 32;
+  if (q_out8 != nullptr && p.splits > 1) return -8;       // the merge pass writes bf16: use the stand-alone quantiser
   const int qblocks = (max_q + QB - 1) / QB;
   int rc;
   switch (head_dim) {

@@ -273,7 +273,7 @@ int64_t get_attn_tc_min_q() { return g_attn_tc_min_q; }
 void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& out,
                const Tensor& block_table, const Tensor& q_start, const Tensor& q_len, const Tensor& kv_len,
                const OptT& ws, int64_t max_q, int64_t n_q, int64_t n_kv, int64_t head_dim, int64_t window,
-               double softcap, int64_t splits, int64_t use_tc) {
+               double softcap, int64_t splits, int64_t use_tc, int64_t fq_out, int64_t fq_sf, int64_t fq_bn) {
   check_bf16(q, "q");
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(block_table.scalar_type() == at::kInt && q_len.scalar_type() == at::kInt, "int32 metadata expected");
@@ -297,10 +297,12 @@ void attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, co
                                    static_cast<int>(block_table.size(1)), static_cast<int>(q.size(0)),
                                    static_cast<int>(k_cache.size(0)), static_cast<int>(n_q), static_cast<int>(n_kv),
                                    static_cast<int>(head_dim), static_cast<int>(window), static_cast<float>(softcap),
-                                   static_cast<int>(splits), ptr_or_null<float>(ws), cur_stream()),
+                                   static_cast<int>(splits), ptr_or_null<float>(ws), as_ptr<void>(fq_out), as_ptr<void>(fq_sf),
+                                   static_cast<int>(fq_bn), cur_stream()),
           "attention_tc");
     return;
   }
+  TORCH_CHECK(fq_out == 0, "fused output quantisation needs the tcgen05 attention kernel");
   if (splits > 1) {
     TORCH_CHECK(ws.has_value(), "split-KV needs a workspace");
     const int64_t R = b2b::attn_rows(static_cast<int>(n_q / n_kv), 1);
