@@ -174,7 +174,24 @@ class P2PNode:
             except Exception as exc:
                 logger.error(f"Monitoring error: {exc}")
 
+    async def _refresh_local_services(self) -> None:
+        """A local service whose engine lost its GPU mesh announces itself unhealthy: peers (and we) sort it last."""
+        mine = self.providers.setdefault(self.peer_id, {})
+        for name, svc in list(self.local_services.items()):
+            try:
+                meta = svc.get_metadata()
+            except Exception:
+                continue
+            was = (mine.get(name) or {}).get("healthy", True)
+            mine[name] = meta
+            if meta.get("healthy", True) != was:
+                logger.warning(f"service '{name}' is now {'healthy' if meta.get('healthy', True) else 'UNHEALTHY (GPU mesh aborted)'}")
+                await self._broadcast(P.service_announce(name, meta))
+        mine["health"] = "good" if all((m or {}).get("healthy", True) for k, m in mine.items()
+                                       if not k.startswith("_") and isinstance(m, dict)) else "degraded"
+
     async def _run_health_checks(self) -> None:
+        await self._refresh_local_services()
         metrics = get_system_metrics()
         stamp = now_ms()
         dead: List[str] = []
@@ -638,7 +655,8 @@ class P2PNode:
                     continue
                 if model_name in (meta.get("models") or []):
                     lat = svcs.get("_latency")
-                    cands.append((svcs.get("health") == "degraded", float(meta.get("price_per_token", 0.0) or 0.0),
+                    cands.append((svcs.get("health") == "degraded" or meta.get("healthy") is False,
+                                  float(meta.get("price_per_token", 0.0) or 0.0),
                                   99999.0 if lat is None else float(lat), pid, name))
                     break
         if not cands:

@@ -116,7 +116,13 @@ class HFService(BaseService):
 
         return {"models": [self.model_name], "price_per_token": self.price_per_token,
                 "max_new_tokens": self.max_new_tokens, "backend": "b200-native", "pieces": self.pieces,
-                "weights": WEIGHT_SOURCE.get(self.model_name, "unloaded")}
+                "weights": WEIGHT_SOURCE.get(self.model_name, "unloaded"), "healthy": self.healthy()}
+
+    def healthy(self) -> bool:
+        """False once the engine's GPU mesh aborted (a peer piece stalled or died): the provider must stop attracting
+        requests -- the reference's semantics for a lost peer (p2p_runtime.py:396-410: dropped, next pick skips it)."""
+        eng = getattr(self.model, "engine", None)
+        return not (eng is not None and getattr(eng, "broken", None))
 
     def _args(self, params: Dict[str, Any]):
         prompt = params.get("prompt")

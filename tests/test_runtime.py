@@ -233,3 +233,37 @@ def test_websocket_transport_wire_compat():
             await node.stop()
 
     run(go())
+
+
+def test_unhealthy_service_is_announced_and_sorted_last():
+    """a provider whose GPU mesh aborted (engine.broken -> service metadata healthy = False) tells the mesh at
+    the next health tick; every node's pick_provider then prefers the healthy replica even if it is more expensive
+    (the reference can only drop peers whose socket closed, p2p_runtime.py:396-410)."""
+    async def go():
+        a, b, c = await mesh(3)
+        try:
+            class Flaky(EchoService):
+                ok = True
+
+                def get_metadata(self):
+                    return {**super().get_metadata(), "healthy": self.ok}
+
+            cheap = Flaky(price=0.0)
+            await a.add_service(cheap)
+            await b.add_service(EchoService(price=1.0))
+            await b.connect_bootstrap(a.addr)
+            await c.connect_bootstrap(a.addr)
+            await settle(lambda: len(c.providers) >= 2 and len(a.providers) >= 2)
+            assert c.pick_provider("echo-model")[0] == a.peer_id           # cheapest wins while healthy
+            cheap.ok = False                                               # "mesh aborted"
+            await settle(lambda: c.providers.get(a.peer_id, {}).get("hf", {}).get("healthy") is False, timeout=5.0)
+            assert c.pick_provider("echo-model")[0] == b.peer_id
+            assert a.pick_provider("echo-model")[0] == b.peer_id and a.providers[a.peer_id]["health"] == "degraded"
+            cheap.ok = True                                                # supervisor restarted the mesh
+            await settle(lambda: c.providers[a.peer_id]["hf"].get("healthy") is True, timeout=5.0)
+            assert c.pick_provider("echo-model")[0] == a.peer_id
+        finally:
+            for n in (a, b, c):
+                await n.stop()
+
+    run(go())
