@@ -75,10 +75,15 @@ class ClockSampler:
     def __init__(self, gpu_index: int = 0):
         self.gpu_index, self.proc, self.lines = gpu_index, None, []
 
+    def mark(self):
+        """index of the next sample: everything from here on belongs to the timed region"""
+        self.first = len(self.lines)
+
     def start(self):
+        self.first = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "25", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -97,7 +102,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], 0, set()
-        for ln in self.lines:
+        region = self.lines[getattr(self, "first", 0):] or self.lines[-1:]      # (a region shorter than one period: the sample right before it)
+        for ln in region:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -200,6 +206,9 @@ def run_ours(args):
         barrier_sync()
         ttfts.append(max_over_ranks(e0.elapsed_time(e1), dev))
         runner.release([0])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                    # nvidia-smi needs ~0.2 s to come up: start it before the warm-up steps
     runner.prefill(seqs)
     runner.decode(W)
     runner.sync()
@@ -207,10 +216,8 @@ def run_ours(args):
     launches0 = runner.kernel_launches
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     flush.fill_(1)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier_sync()
+    sampler.mark()                         # clocks are reported from the samples taken during the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(runner.stream)
     runner.decode(K)
