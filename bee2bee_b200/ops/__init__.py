@@ -108,11 +108,9 @@ def pick_prefill_tile(n_out: int, m_tok: int):
 #: applies to bf16 GEMMs with token tiles of 128 / 256 and no split-K, everything else ignores it
 GEMM_MC = int(os.environ.get("B2B_GEMM_MC", "0"))
 
-#: weight k-blocks (128 rows x 128 B each) a GEMM CTA prefetches into L2 ahead of its shared-memory ring while it
-#: waits for its producer kernel.  MEASURED NEGATIVE on B200 (profiles/l2_prefetch.md: 99.6 -> 102..115 us per layer):
-#: the prefetch flood delays the latency-bound kernel it overlaps with (attention, split-K epilogues) by more than the
-#: L2 hits save, so the default is 0 = off.  +1024: up front only, +2048: LSU prefetch, +4096: no evict_first on W.
-L2_PREFETCH = int(os.environ.get("B2B_L2_PREFETCH", "0"))
+#: L2 weight prefetch: built, measured negative and REMOVED from the kernel in round 2 (profiles/l2_prefetch.md; even
+#: switched off its code and parameters cost ~20 us per decode step).  The value is accepted and ignored.
+L2_PREFETCH = 0
 
 #: shared-memory ring depth of the decode GEMMs (0 = per-token-tile default); fewer stages -> more CTAs per SM, so the
 #: next kernel of a PDL chain becomes resident (and prefetches its weights) while the current one still runs

@@ -75,15 +75,13 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.m_tok = static_cast<int>(x.size(0));
   p.n_out = static_cast<int>(w.size(0));
   p.k = static_cast<int>(w.size(1));
-  p.splitk = static_cast<int>(splitk);
-  p.epi = static_cast<int>(epi);
+  p.splitk = static_cast<int8_t>(splitk);
+  p.epi = static_cast<int8_t>(epi);
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.act_gelu = act_gelu ? 1 : 0;
   p.fp8 = fp8 ? 1 : 0;
-  p.stages = static_cast<int>(stages);
-  p.pf_tiles = static_cast<int>(pf_tiles % 1024);
-  p.pf_mode = static_cast<int>(pf_tiles / 1024);     // tuning: bits 0-1 prefetch variant, bit 2 = weights loaded without evict_first
-  p.mc = static_cast<int>(mc);      // experimental TMA-multicast cluster (0/1 = off)
+  p.stages = static_cast<int8_t>(stages);
+  p.mc = static_cast<int8_t>(mc);      // experimental TMA-multicast cluster (0/1 = off)
   p.w_scale = ptr_or_null<const float>(w_scale);
   p.sfa = fp8 ? ptr_or_null<const uint8_t>(sfa) : nullptr;
   p.sfb = fp8 ? ptr_or_null<const uint8_t>(sfb) : nullptr;
@@ -93,7 +91,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.q_out8 = as_ptr<uint8_t>(q_out8);
   p.q_sf = as_ptr<uint8_t>(q_sf);
   p.ld_q = static_cast<int>(ld_q);
-  p.q_bn = static_cast<int>(q_bn > 0 ? q_bn : 32);
+  p.q_bn = static_cast<int16_t>(q_bn > 0 ? q_bn : 32);
   p.sumsq_out = as_ptr<float>(sumsq_out);
   p.zero_buf = as_ptr<float>(zero_buf);
   p.sumsq = as_ptr<const float>(sumsq);
@@ -111,9 +109,9 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.v_cache = ptr_or_null<__nv_bfloat16>(v_cache);
   p.positions = ptr_or_null<const int>(positions);
   p.slots = ptr_or_null<const int>(slots);
-  p.n_q_heads = static_cast<int>(n_q_heads);
-  p.n_kv_heads = static_cast<int>(n_kv_heads);
-  p.head_dim = static_cast<int>(head_dim);
+  p.n_q_heads = static_cast<int16_t>(n_q_heads);
+  p.n_kv_heads = static_cast<int16_t>(n_kv_heads);
+  p.head_dim = static_cast<int16_t>(head_dim);
   p.rope_theta = static_cast<float>(rope_theta);
   p.q_scale = static_cast<float>(q_scale);
   p.wait_flag = as_ptr<const uint32_t>(wait_flag);
@@ -124,7 +122,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
   p.free_flag = as_ptr<const uint32_t>(free_flag);
   p.bump_epoch = as_ptr<uint32_t>(bump_epoch);
   p.ack_flag = as_ptr<uint32_t>(ack_flag);
-  p.free_lag = static_cast<uint32_t>(free_lag);
+  p.free_lag = static_cast<uint8_t>(free_lag);
   p.dbg = as_ptr<unsigned long long>(dbg);
   if (p.epi == b2b::EPI_QKV_ROPE) {
     TORCH_CHECK(p.q_out && p.k_cache && p.v_cache && p.slots, "qkv epilogue needs q_out/k_cache/v_cache/slots");
@@ -134,7 +132,7 @@ void gemm(const Tensor& w, const Tensor& x, int64_t out_ptr, int64_t ld_out, int
     TORCH_CHECK(p.n_out == (p.n_q_heads + 2 * p.n_kv_heads) * p.head_dim, "qkv rows mismatch");
   }
   if (p.epi == b2b::EPI_RESIDUAL) TORCH_CHECK(p.residual != nullptr, "residual epilogue needs residual");
-  if (p.epi == b2b::EPI_GLU) TORCH_CHECK(p.out != nullptr || p.q_out8 != nullptr, "GLU epilogue needs an output");
+  if (p.epi == b2b::EPI_GLU) TORCH_CHECK(p.out != nullptr || (p.q_out8 != nullptr && p.sfa != nullptr), "GLU epilogue needs an output");
   if (p.signal_flag || p.bump_epoch) TORCH_CHECK(p.done_counter != nullptr, "handoff needs done_counter");
   check(b2b::launch_gemm_tc(p, w.data_ptr(), x.data_ptr(), static_cast<int>(bn), cur_stream()), "gemm_tc");
 }

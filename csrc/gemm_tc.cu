@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint64_t pol_w = (p.pf_mode & 4) ? l2_policy_evict_last() : l2_policy_evict_first();   // weights: streamed once
+      const uint64_t pol_w = l2_policy_evict_first();   // weights: streamed once
       const uint64_t pol_x = l2_policy_evict_last();    // activations: re-read by every CTA
       // Weight tiles depend on no earlier kernel: fill the ring with them first, THEN wait for
       // the producer of the activations (previous kernel via PDL, upstream piece via its flag).
@@ -172,15 +172,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_arrive_expect_tx(&full_bar[i], TX_BYTES);
         tma_load_2d_hint(smem + i * STAGE_BYTES, &tmap_w, &full_bar[i], (kb_begin + i) * BKE, tile_n * BM, pol_w);
         if constexpr (MX) bulk_load(sf_s + i * Cfg::kSfBytes, sfa_g + static_cast<size_t>(i) * Cfg::kSfaBytes, Cfg::kSfaBytes, &full_bar[i]);
-      }
-      // ... and keep HBM streaming while we wait: L2 prefetch of the next `pf` weight k-blocks behind the ring.  The
-      // kernel boundary (previous epilogue / split-K reduce / flag hop / our own 1/rms pass) otherwise leaves HBM idle
-      // for 5-8 us per GEMM; the ring alone only covers STAGES x 16 KB per CTA.
-      const int pf = ((p.pf_mode & 3) == 2) ? 0 : p.pf_tiles;
-      const bool pf_roll = (p.pf_mode & 3) == 0;
-      {
-        const int pf_first = (nkb < npre + pf) ? nkb : npre + pf;
-        for (int i = npre; i < pf_first; ++i) tma_prefetch_l2_2d(&tmap_w, (kb_begin + i) * BKE, tile_n * BM);
       }
       pdl_wait();
       if (p.wait_flag != nullptr) {
@@ -203,7 +194,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       int s = 0;                 // kb % STAGES
       uint32_t ph = 1;           // (kb / STAGES) & 1 -- first refill round
       for (; kb < nkb; ++kb) {
-        if (pf_roll && pf > 0 && kb + pf < nkb) tma_prefetch_l2_2d(&tmap_w, (kb_begin + kb + pf) * BKE, tile_n * BM);
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
         tma_load_2d_hint(smem + s * STAGE_BYTES, &tmap_w, &full_bar[s], (kb_begin + kb) * BKE,
@@ -266,15 +256,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     // Every CTA of a split-K cluster finishes its own slice of token columns [col0, col0 + ncol)
     // (reduce-scatter, see below), so each CTA only needs the per-token inputs of that slice.
     const int et = threadIdx.x - 64;   // 0..127
-    if ((p.pf_mode & 3) == 2 && p.pf_tiles > 0) {
-      // LSU variant of the L2 weight prefetch: thread `et` owns weight row `et` of the tile
-      const int npre = nkb < STAGES ? nkb : STAGES;
-      const int last = (nkb < npre + p.pf_tiles) ? nkb : npre + p.pf_tiles;
-      const uint8_t* rowp = reinterpret_cast<const uint8_t*>(p.w_base) +
-                            (static_cast<size_t>(tile_n) * BM + et) * static_cast<size_t>(p.k) * (FP8 ? 1 : 2);
-      for (int j = npre; j < last; ++j)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + static_cast<size_t>(kb_begin + j) * ROW_BYTES));
-    }
     pdl_wait();                        // everything below reads / writes memory of earlier kernels
     {
       if constexpr (EPI == EPI_QKV_ROPE) {
@@ -335,13 +316,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         for (int t = col0 + et; t < col0 + ncol; t += 128) {
           const int tok = tok0 + t;
           float r = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
-          if (p.sumsq != nullptr && tok < p.m_tok)      // RMSNorm statistics accumulated by the producing GEMM's epilogue
-            r *= rsqrtf(p.sumsq[tok] / static_cast<float>(p.k) + p.eps);
+          if constexpr (MX) {
+            if (p.sumsq != nullptr && tok < p.m_tok)      // RMSNorm statistics accumulated by the producing GEMM's epilogue
+              r *= rsqrtf(p.sumsq[tok] / static_cast<float>(p.k) + p.eps);
+          }
           rstd_s[t] = r;
         }
-        if (p.zero_buf != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
-          for (int t = et; t < BN; t += 128)
-            if (tok0 + t < p.m_tok) p.zero_buf[tok0 + t] = 0.f;
+        if constexpr (MX) {
+          if (p.zero_buf != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
+            for (int t = et; t < BN; t += 128)
+              if (tok0 + t < p.m_tok) p.zero_buf[tok0 + t] = 0.f;
+        }
       }
       epi_bar_sync();
     }
@@ -423,8 +408,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     // (32 lanes = 32 consecutive features = one MX block per token).  The per-token block maximum and sum of squares are
     // computed with a transpose-reduce (8 + 4 + 2 + 1 + 1 shuffles for all 16 tokens instead of 5 dependent shuffles per
     // token): afterwards lanes 2t and 2t+1 hold the totals of token t.
-    const int q_nkc = p.ld_q >> 7;
-    const int q_chunk = p.q_bn > 128 ? 1024 : 512;
+    const int q_nkc = MX ? (p.ld_q >> 7) : 0;
+    const int q_chunk = (MX && p.q_bn > 128) ? 1024 : 512;
     auto emit_q_chunk = [&](const float* qv, int tok_base, int nvalid, int feat) {
       float r[16], am[16], ss[16];
 #pragma unroll
@@ -550,16 +535,20 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
           if (p.out2 != nullptr)
             reinterpret_cast<__nv_bfloat16*>(p.out2)[static_cast<size_t>(tok) * p.ld_out + n_glob] = r16;
-          qv[i] = rv;
-          q_valid = i + 1;
+          if constexpr (MX) {      // (anything of the fused quantiser left in the bf16 instantiations cost 50 us per step)
+            qv[i] = rv;
+            q_valid = i + 1;
+          }
         } else if constexpr (EPI == EPI_GLU) {
           const float u = xch[(c + i) * 64 + row] * rs * wsc_up;
           const float g = p.act_gelu ? gelu_tanh(a) : silu(a);
-          if (p.out != nullptr)
+          if (!MX || p.out != nullptr)
             reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(tok) * p.ld_out + tile_n * 64 + row] =
                 __float2bfloat16_rn(g * u);
-          qv[i] = g * u;
-          q_valid = i + 1;
+          if constexpr (MX) {
+            qv[i] = g * u;
+            q_valid = i + 1;
+          }
         } else {   // EPI_QKV_ROPE
           float o = a;
           if (sect < 2 && p.rope_theta > 0.f) {
@@ -803,7 +792,6 @@ int gemm_tc_max_splitk(int bn, int epi, int stages) {
 
 int launch_gemm_tc(const GemmParams& p_in, const void* w, const void* x, int bn, cudaStream_t stream) {
   GemmParams p = p_in;
-  p.w_base = w;
   const int elt = p.fp8 ? 1 : 2;
   const int bke = ROW_BYTES / elt;
   if (p.n_out % BM != 0 || p.k % bke != 0 || p.m_tok <= 0) return -2;

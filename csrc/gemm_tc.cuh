@@ -19,16 +19,13 @@ struct GemmParams {
   int m_tok;          // rows of X
   int n_out;          // rows of W (multiple of 128)
   int k;              // multiple of 64
-  int splitk;         // cluster size along grid.z (1..8)
-  int epi;
-  int out_fp32;       // EPI_PLAIN only: write fp32 (logits)
-  int act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
-  int fp8;            // operands are e4m3 (W8A8): W [N,K] and X [T,K] one byte per element
-  int stages;         // shared-memory ring depth (0 = the token tile's default)
-  int pf_mode;        // tuning: 0 = TMA prefetch up front + rolling, 1 = TMA up front only, 2 = LSU prefetch.global.L2 by the epilogue warps
-  int pf_tiles;       // weight k-blocks prefetched into L2 ahead of the shared-memory ring (0 = off)
-  int mc;             // EXPERIMENTAL (0/1 = off): cluster of `mc` CTAs along the weight-tile axis shares the token tile by TMA multicast
-  const void* w_base;    // weight matrix base (LSU prefetch variant)
+  int8_t splitk;         // cluster size along grid.z (1..8)
+  int8_t epi;
+  int8_t out_fp32;       // EPI_PLAIN only: write fp32 (logits)
+  int8_t act_gelu;       // EPI_GLU: 0 = SiLU (SwiGLU), 1 = tanh-GELU (GeGLU)
+  int8_t fp8;            // operands are e4m3 (W8A8): W [N,K] and X [T,K] one byte per element
+  int8_t stages;         // shared-memory ring depth (0 = the token tile's default)
+  int8_t mc;             // EXPERIMENTAL (0/1 = off): cluster of `mc` CTAs along the weight-tile axis shares the token tile by TMA multicast
   const float* w_scale;  // fp8: per-output-row dequant scale [n_out] (activation scale rides in `rstd`)
   // MX fp8 (tcgen05 kind::mxf8f6f4.block_scale): UE8M0 scale per 32 K elements, pre-arranged in 512-byte
   // chunks per (128 rows, 128 K): byte (r % 32) * 16 + (r / 32) * 4 + (k / 32) % 4.  sfa: weights
@@ -57,7 +54,7 @@ struct GemmParams {
   uint8_t* q_out8;                // [m_tok, ld_q] e4m3, or null
   uint8_t* q_sf;                  // scale-factor chunks of the consumer GEMM's activation operand
   int ld_q;                       // row stride of q_out8 in elements (= consumer K)
-  int q_bn;                       // consumer token tile (chunk layout), >= 32
+  int16_t q_bn;                   // consumer token tile (chunk layout), >= 32
   float* sumsq_out;               // [m_tok] += sum over this CTA's features of out^2, or null
   float* zero_buf;                // [m_tok] accumulator to clear (read by an earlier GEMM, re-filled by a later one), or null
   const float* sumsq;             // consumer side: per-token sum of squares of X -> rstd = rsqrt(sumsq / k + eps)
@@ -68,7 +65,7 @@ struct GemmParams {
   __nv_bfloat16* v_cache;
   const int* positions;           // [m_tok]
   const int* slots;               // [m_tok] physical KV slot of each token
-  int n_q_heads, n_kv_heads, head_dim;
+  int16_t n_q_heads, n_kv_heads, head_dim;
   float rope_theta;               // <=0: no rotary
   float q_scale;                  // folded softmax scale applied to q (1.0 = none)
 
@@ -85,7 +82,7 @@ struct GemmParams {
   uint32_t* signal_epoch;         // local: number of handoffs already published on this slot
   uint32_t* done_counter;         // local, self-resetting
   const uint32_t* free_flag;      // local: consumer's ack (it has released `*free_flag` payloads of this slot)
-  uint32_t free_lag;              // payloads that may be outstanding: 0 = single staging buffer, 1 = double-buffered
+  uint8_t free_lag;               // payloads that may be outstanding: 0 = single staging buffer, 1 = double-buffered
   uint32_t* bump_epoch;           // local: this piece's input-slot epoch (incremented once)
   uint32_t* ack_flag;             // peer: upstream producer's free_flag for our input slot
 
