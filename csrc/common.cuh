@@ -318,9 +318,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Spin until *flag >= target (monotonic counters; wrap-safe compare); bounded, see above.
-__device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t target) {
-  if (static_cast<int32_t>(ld_acquire_sys(flag) - target) >= 0) return;          // fast path: already published
+// Slow path of a flag wait: out of line on purpose -- the decode GEMMs are sensitive to their code size (a bisect in
+// round 2 attributed 1-2 % of the step to a few hundred extra SASS instructions per kernel), and this is inlined nowhere.
+static __device__ __noinline__ void wait_flag_slow(const uint32_t* flag, uint32_t target) {
   volatile uint32_t* ab = g_abort_word;
   if (ab != nullptr && *ab != 0u) return;                                        // mesh aborted: drain
   uint32_t spins = 0;
@@ -343,6 +343,12 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t targ
       __trap();
     }
   }
+}
+
+// Spin until *flag >= target (monotonic counters; wrap-safe compare); bounded, see above.
+__device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t target) {
+  if (static_cast<int32_t>(ld_acquire_sys(flag) - target) >= 0) return;          // fast path: already published
+  wait_flag_slow(flag, target);
 }
 
 // Programmatic dependent launch: wait for (and see the memory of) all prerequisite grids /
