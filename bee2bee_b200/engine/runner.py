@@ -116,7 +116,8 @@ class GpuRunner:
                                  self.max_chunk_seqs, num_pages, quant=quant, units=self.units)
         del tensors
         self.mesh = MeshComm(rank, world, self.device, cfg.hidden_size, max_tokens, groups, self.gb, self.hist_len,
-                             control_group, ffn=cfg.ffn_size if mlp_cut else 0)
+                             control_group, ffn=cfg.ffn_size if mlp_cut else 0,
+                             mx=bool(getattr(self.piece, "mx_hand", False)))
         self.C = ops.native()
         dev, i32 = self.device, torch.int32
         B = max_batch
@@ -180,7 +181,10 @@ class GpuRunner:
         return t[g * self.gb:(g + 1) * self.gb]
 
     def launches_per_decode_step(self) -> int:
-        """Native kernel launches one rank issues per group decode step (for reporting)."""
+        """Native kernel launches one rank issues per group decode step: counted while the decode graph was recorded
+        (``ops.LAUNCHES``); before the first capture, an estimate from the layer structure."""
+        if getattr(self, "_decode_launches", 0):
+            return self._decode_launches
         c, n = self.cfg, len(self.layers)
         if c.norm == "ln":
             per = 9
@@ -347,8 +351,10 @@ class GpuRunner:
                     body()
                     self.stream.synchronize()
                 g = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES[0]
                 with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
                     body()
+                st["launches"] = ops.LAUNCHES[0] - n0        # kernels recorded into this chunk graph
                 st["graph"] = g
         self._pf[key] = st
         return st
@@ -396,7 +402,7 @@ class GpuRunner:
         else:
             st["body"]()
         self.pf_chunks += 1
-        self.kernel_launches += self.launches_per_decode_step() + 1
+        self.kernel_launches += st.get("launches") or (self.launches_per_decode_step() + 1)
 
     # ------------------------------------------------------------------- decode
     def _decode_group(self, g: int) -> None:
@@ -436,6 +442,7 @@ class GpuRunner:
         # boundaries (the first kernel of group g+1 becomes resident under the tail of group g) and a step costs one
         # graph launch instead of `groups`.  B2B_GRAPH_PER_GROUP=1 restores one graph per group.
         per_group = os.environ.get("B2B_GRAPH_PER_GROUP", "0") == "1"
+        n0 = ops.LAUNCHES[0]
         with torch.cuda.stream(self.stream):
             if per_group:
                 for g in range(self.groups):
@@ -449,6 +456,7 @@ class GpuRunner:
                     for g in range(self.groups):
                         self._decode_group(g)
                 self.graphs[-1] = graph
+        self._decode_launches = (ops.LAUNCHES[0] - n0) // self.groups      # kernels recorded per group step
         self.stream.synchronize()
 
     def warmup(self) -> None:

@@ -51,6 +51,21 @@ class Handoff:
     free_lag: int = 0        # payloads that may be outstanding on the output slot (1 = double-buffered staging)
     pf_flag: int = 0         # piece 0, decode: counter of prefill chunks completed by the last piece (local)
     pf_need: int = 0         # piece 0, decode: u32 word = chunks that must be complete before this group may embed
+    # mxfp8, quantisation fused ACROSS the hop: the producer's tail GEMM (O-proj / down, residual epilogue) also emits the
+    # e4m3 copy of the residual stream, its UE8M0 scale-factor chunks and the per-token sum of squares straight into the
+    # consumer's memory; the consumer's first GEMM (QKV / gate-up) TMA-loads them after acquiring the hop flag
+    in_q: int = 0            # [max_tokens, H] e4m3 (local)
+    in_sf: int = 0           # scale-factor chunks of in_q (local)
+    in_ss: int = 0           # [max_tokens] fp32 sum of squares (local; zeroed by the consumer after use)
+    out_q: int = 0           # downstream in_q / in_sf / in_ss (peer)
+    out_sf: int = 0
+    out_ss: int = 0
+    # ... and for a cut between gate/up and down: the GLU epilogue stores the e4m3 MLP hidden + scale factors INSTEAD of
+    # the bf16 hidden (half the bytes on the link); the consumer's down GEMM TMA-loads them
+    in_qh: int = 0           # [max_tokens, F] e4m3 (local)
+    in_sfh: int = 0
+    out_qh: int = 0          # downstream in_qh / in_sfh (peer)
+    out_sfh: int = 0
 
 
 @dataclass
@@ -101,6 +116,7 @@ class NativePiece:
         self.fp8 = quant in ("fp8", "mxfp8") and self.fused_norm and not cfg.post_norms and cfg.glu
         self.mx = self.fp8 and quant == "mxfp8"
         self.mx_fuse = False
+        self.mx_hand = False         # mxfp8: the quantised residual stream crosses the piece handoff (set with mx_fuse)
         self.wscale: Dict[str, torch.Tensor] = {}
         c = cfg
         assert c.hidden_size % 128 == 0 or c.hidden_size % 64 == 0, "hidden must be a multiple of 64"
@@ -175,6 +191,10 @@ class NativePiece:
                 # stream for the next RMSNorm-fused GEMM (+ per-token sum of squares), the gate/up epilogue emits the
                 # e4m3 MLP hidden for the down GEMM -- 3 of the 4 activation-quantiser launches of a layer disappear
                 self.mx_fuse = os.environ.get("B2B_MX_FUSE", "1") == "1"
+                # ... and ACROSS the handoff (B2B_MX_HANDOFF, default on): a tail O-proj / down GEMM emits that e4m3 copy,
+                # the scale-factor chunks and the sum of squares into the downstream piece's memory together with the
+                # bf16 residual stream; the downstream head GEMM consumes them (no quantiser launch at a piece head)
+                self.mx_hand = self.mx_fuse and os.environ.get("B2B_MX_HANDOFF", "1") == "1"
                 H, F = cfg.hidden_size, cfg.ffn_size
                 self._fq_x = torch.zeros((rows, H), device=self.device, dtype=torch.float8_e4m3fn)
                 self._fq_h = torch.zeros((rows, F), device=self.device, dtype=torch.float8_e4m3fn)
@@ -298,6 +318,33 @@ class NativePiece:
         fuse = self.mx_fuse
         q_bn = ops.pick_bn_mx(T) if fuse else 0
         xq_ready = False       # the residual stream entering the next attention block has a fused e4m3 copy (+ sumsq1)
+        # quantised payload of the hop (see Handoff.in_q): consumed by a QKV / gate-up head GEMM, produced by an
+        # O-proj / down tail GEMM.  A cut between gate/up and down keeps the bf16 MLP hidden + consumer-side quantiser.
+        tfp = ops.native().tensor_from_ptr if self.mx_hand else None
+        H = c.hidden_size
+        in_q = in_sf = in_ss = None
+        if self.mx_hand and not self.first and hand.in_q and wait_flag and self.head_mode in (0, 1):
+            di = self.device.index
+            in_q = tfp(hand.in_q, [T, H], "u8", di).view(torch.float8_e4m3fn)
+            in_sf = tfp(hand.in_sf, [((T + 31) // 32) * (H // 128) * 512], "u8", di)
+            in_ss = tfp(hand.in_ss, [T], "f32", di)
+        out_fq = {}
+        if self.mx_hand and not self.last and hand.out_q and hand.out_x and self.tail_mode in (0, 2):
+            di = self.device.index
+            out_fq = dict(fq_out=tfp(hand.out_q, [T, H], "u8", di).view(torch.float8_e4m3fn),
+                          fq_sf=tfp(hand.out_sf, [((T + 31) // 32) * (H // 128) * 512], "u8", di), fq_bn=q_bn,
+                          sumsq_out=tfp(hand.out_ss, [T], "f32", di))
+        F = c.ffn_size
+        in_qh = in_sfh = None          # quantised MLP hidden of a gate/up | down cut
+        if self.mx_hand and not self.first and hand.in_qh and wait_flag and self.head_mode == 2:
+            di = self.device.index
+            in_qh = tfp(hand.in_qh, [T, F], "u8", di).view(torch.float8_e4m3fn)
+            in_sfh = tfp(hand.in_sfh, [((T + 31) // 32) * (F // 128) * 512], "u8", di)
+        out_fqh = {}
+        if self.mx_hand and not self.last and hand.out_qh and hand.out_x and self.tail_mode == 1:
+            di = self.device.index
+            out_fqh = dict(fq_out=tfp(hand.out_qh, [T, F], "u8", di).view(torch.float8_e4m3fn),
+                           fq_sf=tfp(hand.out_sfh, [((T + 31) // 32) * (F // 128) * 512], "u8", di), fq_bn=q_bn, no_out=True)
         for li, l in enumerate(self.layers):
             p = f"l{l}."
             do_attn, do_gu, do_down = self.has_attn(l), self.has_gu(l), self.has_down(l)
@@ -318,7 +365,7 @@ class NativePiece:
             if not do_attn:
                 x2 = x                  # the upstream piece ran this layer's attention: x is the post-attention stream
             elif self.fused_norm:
-                if head_wait and not inline:
+                if head_wait and not inline and in_q is None:
                     # wide token tiles use a separate 1/rms kernel that reads the peer-written rows:
                     # acquire the handoff flag first (the GEMM's own wait then passes immediately)
                     ops.native().flag_wait(head_wait, head_epoch, 1)
@@ -331,6 +378,11 @@ class NativePiece:
                     ops.gemm(self.w[p + "wqkv"], self._fq_x[:T], sfb=self._fq_sf_x, sumsq=self._sumsq1,
                              **self._wkw(p + "wqkv"), **qkv_kw)
                     xq_ready = False
+                elif self.fp8 and head_wait and in_q is not None:
+                    # piece head: the upstream tail GEMM stored the e4m3 copy, scale factors and sum of squares here; the
+                    # GEMM acquires the hop flag itself (weights stream while it waits)
+                    ops.gemm(self.w[p + "wqkv"], in_q, sfb=in_sf, sumsq=in_ss, wait_flag=head_wait, wait_epoch=head_epoch,
+                             **self._wkw(p + "wqkv"), **qkv_kw)
                 elif self.fp8:
                     if head_wait and inline:
                         ops.native().flag_wait(head_wait, head_epoch, 1)     # the quant kernel reads x first
@@ -376,9 +428,12 @@ class NativePiece:
                     x2_fused = fuse and do_gu and do_down          # this layer's gate/up and down run here
                     fq = {}
                     if fuse:
-                        fq = dict(zero_buf=self._sumsq1)
+                        # (layer 0 of a piece fed by a quantised hop: its QKV read the hop's sum of squares, not sumsq1)
+                        fq = dict(zero_buf=in_ss if (li == 0 and in_ss is not None) else self._sumsq1)
                         if x2_fused:
                             fq.update(fq_out=self._fq_x[:T], fq_sf=self._fq_sf_x, fq_bn=q_bn, sumsq_out=self._sumsq2)
+                        elif okw is tail_kw and tail_kw and out_fq:
+                            fq.update(out_fq)            # tail O-proj: quantised copy for the next piece's gate/up GEMM
                     ops.gemm(self.w[p + "wo"], aq, out=o_out, epi=ops.EPI_RESIDUAL, residual=x, **akw,
                              **self._wkw(p + "wo"), **okw, **fq)
                 else:
@@ -390,7 +445,9 @@ class NativePiece:
             # ---------------- MLP block
             mlp_wait = head_wait if not do_attn else 0      # piece starts inside this layer: its first GEMM consumes the input
             mlp_epoch = head_epoch if not do_attn else 0
-            if mlp_wait and (self.fp8 or not inline):
+            mlp_q_head = bool(mlp_wait) and do_gu and in_q is not None     # gate/up head GEMM fed by a quantised hop
+            down_q_head = bool(mlp_wait) and not do_gu and in_qh is not None   # down head GEMM fed by a quantised hop
+            if mlp_wait and (self.fp8 or not inline) and not (mlp_q_head or down_q_head):
                 ops.native().flag_wait(mlp_wait, mlp_epoch, 1)   # a separate quant / 1/rms kernel reads the input first
             gu_tail = tail_kw if (do_gu and not do_down) else {}   # piece ends after gate/up: it is the tail GEMM
             if gu_tail and hand.out_h:
@@ -401,9 +458,13 @@ class NativePiece:
             elif c.glu and self.fp8:
                 h_fused = fuse and do_down and not gu_tail   # the down GEMM of this layer consumes the e4m3 hidden directly
                 hq_kw = dict(fq_out=self._fq_h[:T], fq_sf=self._fq_sf_h, fq_bn=q_bn, no_out=True) if h_fused else {}
+                if gu_tail and out_fqh:
+                    hq_kw = out_fqh          # tail gate/up GEMM: e4m3 hidden + scale factors into the peer, no bf16 copy
                 if fuse and do_attn and do_down and not c.post_norms:
                     # x2 was quantised by the O-proj epilogue of this layer (sum of squares in sumsq2)
                     x2q, akw = self._fq_x[:T], dict(sfb=self._fq_sf_x, sumsq=self._sumsq2)
+                elif mlp_q_head:
+                    x2q, akw = in_q, dict(sfb=in_sf, sumsq=in_ss, wait_flag=mlp_wait, wait_epoch=mlp_epoch)
                 else:
                     x2q, akw = self._quant(x2, with_rms=True)
                 hmid = ops.gemm(self.w[p + "wgu"], x2q, out=None if (gu_tail or h_fused) else self.h_buf[:T], epi=ops.EPI_GLU,
@@ -442,11 +503,15 @@ class NativePiece:
                 if self.fp8:
                     if h_fused:
                         hq, akw = self._fq_h[:T], dict(sfb=self._fq_sf_h)
+                    elif down_q_head:
+                        hq, akw = in_qh, dict(sfb=in_sfh, wait_flag=down_wait, wait_epoch=down_epoch)
                     else:
                         hq, akw = self._quant(hmid, with_rms=False)
                     fq = {}
                     if fuse:
-                        fq = dict(zero_buf=self._sumsq2)
+                        fq = dict(zero_buf=in_ss if (li == 0 and mlp_q_head) else self._sumsq2)
+                        if tail_kw and out_fq:
+                            fq.update(out_fq)            # tail down GEMM: quantised copy for the next piece's QKV GEMM
                         if li + 1 < n_layers and not tail_kw:
                             # the next layer's QKV GEMM (on this piece) reads the e4m3 copy; its RMSNorm uses sumsq1
                             fq.update(fq_out=self._fq_x[:T], fq_sf=self._fq_sf_x, fq_bn=q_bn, sumsq_out=self._sumsq1)

@@ -20,13 +20,43 @@ NUM_SMS = 148
 
 _C = None
 
+# Kernel launches issued through the extension (eager calls and calls recorded into a CUDA graph alike): every entry
+# point that launches exactly one kernel bumps LAUNCHES[0]; the split-KV attention merge pass is added by
+# ``attention``.  The runner reads the delta around a graph capture, so the launch counts it reports are the kernels
+# that were actually recorded, not a formula.
+LAUNCHES = [0]
+_KERNEL_ENTRY_POINTS = ("add", "attention", "decode_advance", "embed", "fetch_window", "flag_signal", "flag_wait", "gemm",
+                        "kv_append", "layernorm", "mark_seen", "quant_fp8_rows", "quant_mxfp8_rows", "rmsnorm", "sample",
+                        "set_decode_state")
+
+
+class _CountedModule:
+    """The extension module with its kernel entry points wrapped by a launch counter (everything else passes through)."""
+
+    def __init__(self, mod):
+        self._mod = mod
+        for name in dir(mod):
+            if name.startswith("__"):
+                continue
+            fn = getattr(mod, name)
+            setattr(self, name, self._counted(fn) if name in _KERNEL_ENTRY_POINTS and callable(fn) else fn)
+
+    @staticmethod
+    def _counted(fn):
+        def call(*a, **kw):
+            LAUNCHES[0] += 1
+            return fn(*a, **kw)
+        call.__name__ = getattr(fn, "__name__", "kernel")
+        call.__doc__ = getattr(fn, "__doc__", None)
+        return call
+
 
 def native():
     """The compiled extension module; built in-tree by ``__graft_entry__.build()``."""
     global _C
     if _C is None:
         try:
-            _C = importlib.import_module("bee2bee_b200._C")
+            _C = _CountedModule(importlib.import_module("bee2bee_b200._C"))
         except ImportError as e:  # pragma: no cover - exercised only on broken installs
             raise RuntimeError(
                 "bee2bee_b200 native extension is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -343,6 +373,8 @@ def attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, *, 
         use_tc = 1
     native().attention(q, k_cache, v_cache, out, block_table, q_start, q_len, kv_len, ws, max_q, n_q, n_kv, head_dim,
                        window, softcap, splits, use_tc, _ptr(fq_out), _ptr(fq_sf), fq_bn)
+    if splits > 1:
+        LAUNCHES[0] += 1           # split-KV: the merge pass is a second kernel
     return out
 
 

@@ -43,8 +43,11 @@ class MeshComm:
     """Per-rank view of the pipeline ring rank0 -> rank1 -> ... -> rank(W-1) -> rank0 (tokens)."""
 
     def __init__(self, rank: int, world: int, device: torch.device, hidden: int, max_tokens: int, groups: int,
-                 group_batch: int, hist_len: int, control_group=None, ffn: int = 0):
+                 group_batch: int, hist_len: int, control_group=None, ffn: int = 0, mx: bool = False):
         # ffn > 0: some piece boundary lies between a gate/up and a down GEMM -> the hop also carries the MLP hidden
+        # mx: block-scaled fp8 pieces -> the hop also carries the e4m3 copy of the residual stream, its scale-factor
+        #     chunks and the per-token sum of squares (quantisation fused across the handoff)
+        self.mx = mx
         self.rank, self.world, self.device = rank, world, torch.device(device)
         self.hidden, self.max_tokens, self.groups, self.group_batch, self.hist_len = hidden, max_tokens, groups, group_batch, hist_len
         self.control_group = control_group
@@ -62,8 +65,31 @@ class MeshComm:
             self._alloc_and_exchange()
 
     # ------------------------------------------------------------------ set-up
+    def _sf_bytes(self, rows: int, width: int = 0) -> int:
+        """scale-factor chunks of ``rows`` tokens x ``width`` (default hidden) -- worst case: 32-row token tiles,
+        512 B per tile and 128 K"""
+        return ((rows + 31) // 32) * ((width or self.hidden) // 128) * 512
+
     def _sizes(self) -> Dict[str, int]:
+        mxs = {}
+        if self.mx:
+            mxs = {
+                "stage_q": self.groups * self.group_batch * self.hidden,
+                "stage_q_pf": 2 * self.max_tokens * self.hidden,
+                "stage_sf": self.groups * self._sf_bytes(self.group_batch),
+                "stage_sf_pf": 2 * self._sf_bytes(self.max_tokens),
+                "stage_ss": self.groups * self.group_batch * 4,
+                "stage_ss_pf": 2 * self.max_tokens * 4,
+            }
+            if self.ffn:
+                mxs.update({
+                    "stage_qh": self.groups * self.group_batch * self.ffn,
+                    "stage_qh_pf": 2 * self.max_tokens * self.ffn,
+                    "stage_sfh": self.groups * self._sf_bytes(self.group_batch, self.ffn),
+                    "stage_sfh_pf": 2 * self._sf_bytes(self.max_tokens, self.ffn),
+                })
         return {
+            **mxs,
             "stage": self.groups * self.group_batch * self.hidden * 2,          # decode: one bf16 slot per group
             "stage_pf": 2 * self.max_tokens * self.hidden * 2,                  # prefill chunks: double-buffered
             "stage_h": self.groups * self.group_batch * self.ffn * 2,           # MLP hidden of a gate/up | down cut
@@ -139,6 +165,18 @@ class MeshComm:
         h_off = group * self.group_batch * self.ffn * 2
         if self.ffn and not first:
             h.in_h = self.local["stage_h"] + h_off
+        q_off, sf_off, ss_off = group * self.group_batch * self.hidden, group * self._sf_bytes(self.group_batch), tok_off
+        if self.mx and not first:
+            h.in_q, h.in_sf, h.in_ss = self.local["stage_q"] + q_off, self.local["stage_sf"] + sf_off, self.local["stage_ss"] + ss_off
+        if self.mx and not last:
+            h.out_q, h.out_sf, h.out_ss = (self.remote_next["stage_q"] + q_off, self.remote_next["stage_sf"] + sf_off,
+                                           self.remote_next["stage_ss"] + ss_off)
+        if self.mx and self.ffn:
+            qh_off, sfh_off = group * self.group_batch * self.ffn, group * self._sf_bytes(self.group_batch, self.ffn)
+            if not first:
+                h.in_qh, h.in_sfh = self.local["stage_qh"] + qh_off, self.local["stage_sfh"] + sfh_off
+            if not last:
+                h.out_qh, h.out_sfh = self.remote_next["stage_qh"] + qh_off, self.remote_next["stage_sfh"] + sfh_off
         if last:
             h.out_x = self.remote_first["tok"] + tok_off
             h.out_flag = self._flag(self.remote_first, group, F_IN_FLAG)
@@ -163,6 +201,19 @@ class MeshComm:
         h.done = self._flag(self.local, c, F_DONE)
         h.free_lag = 1
         h_off = parity * self.max_tokens * self.ffn * 2
+        q_off, sf_off, ss_off = parity * self.max_tokens * self.hidden, parity * self._sf_bytes(self.max_tokens), parity * self.max_tokens * 4
+        if self.mx and not first:
+            h.in_q, h.in_sf, h.in_ss = (self.local["stage_q_pf"] + q_off, self.local["stage_sf_pf"] + sf_off,
+                                        self.local["stage_ss_pf"] + ss_off)
+        if self.mx and not last:
+            h.out_q, h.out_sf, h.out_ss = (self.remote_next["stage_q_pf"] + q_off, self.remote_next["stage_sf_pf"] + sf_off,
+                                           self.remote_next["stage_ss_pf"] + ss_off)
+        if self.mx and self.ffn:
+            qh_off, sfh_off = parity * self.max_tokens * self.ffn, parity * self._sf_bytes(self.max_tokens, self.ffn)
+            if not first:
+                h.in_qh, h.in_sfh = self.local["stage_qh_pf"] + qh_off, self.local["stage_sfh_pf"] + sfh_off
+            if not last:
+                h.out_qh, h.out_sfh = self.remote_next["stage_qh_pf"] + qh_off, self.remote_next["stage_sfh_pf"] + sfh_off
         if not first:
             h.in_x = self.local["stage_pf"] + off
             if self.ffn:
@@ -222,6 +273,16 @@ class MeshComm:
             flags[:self.groups, F_IN_FLAG] = 1
         if self.rank == self.world - 1:
             flags[:self.groups, F_OUT_EPOCH] = 1
+        if self.mx:
+            sizes = self._sizes()
+            for name in ("stage_q", "stage_q_pf", "stage_qh", "stage_qh_pf"):
+                if name in sizes:
+                    self.local_view(name, (sizes[name],), "u8").zero_()
+            for name in ("stage_sf", "stage_sf_pf", "stage_sfh", "stage_sfh_pf"):
+                if name in sizes:
+                    self.local_view(name, (sizes[name],), "u8").fill_(127)     # 2^0 for rows nobody writes (0xFF would be NaN)
+            for name in ("stage_ss", "stage_ss_pf"):
+                self.local_view(name, (sizes[name] // 4,), "f32").zero_()
         torch.cuda.synchronize(self.device)
         self.barrier()
 

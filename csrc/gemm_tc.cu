@@ -313,6 +313,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           }
         }
       } else {
+        if constexpr (MX) {
+          if (p.sumsq != nullptr && p.wait_flag != nullptr) {
+            // piece head fed by a quantised hop: the sums of squares were accumulated by the upstream piece's tail GEMM
+            const uint32_t target = *reinterpret_cast<const volatile uint32_t*>(p.wait_epoch) + 1;
+            wait_flag_ge(p.wait_flag, target);
+          }
+        }
         for (int t = col0 + et; t < col0 + ncol; t += 128) {
           const int tok = tok0 + t;
           float r = (p.rstd != nullptr && tok < p.m_tok) ? p.rstd[tok] : 1.f;
@@ -450,7 +457,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int tile = tok / p.q_bn, n = tok - tile * p.q_bn, rr = n & 127;
         p.q_sf[(static_cast<size_t>(tile) * q_nkc + (feat >> 7)) * q_chunk + (n >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4 +
                ((feat >> 5) & 3)] = static_cast<uint8_t>(e_mine + 127);
-        if (p.sumsq_out != nullptr) atomicAdd(&p.sumsq_out[tok], ss[0]);
+        if (p.sumsq_out != nullptr) {
+          if (p.signal_flag != nullptr) atomicAdd_system(&p.sumsq_out[tok], ss[0]);   // tail GEMM: the counter lives in the peer's memory
+          else atomicAdd(&p.sumsq_out[tok], ss[0]);
+        }
       }
     };
 

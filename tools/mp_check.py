@@ -89,7 +89,13 @@ else:
     r.sync()
     r.decode(steps - steps // 2)          # second burst: epochs are monotonic, nothing is re-armed in between
     win = r.fetch_window([0] * total, steps + 1)
+    launches = [r.launches_per_decode_step()]          # kernels recorded per group step on each rank
+    if world > 1:
+        import torch.distributed as dist
+        launches = [None] * world
+        dist.all_gather_object(launches, r.launches_per_decode_step())
     if rank == 0:
-        print("RESULT " + json.dumps({"world": world, "tokens": win[:total].tolist(), "chunks": r.pf_chunks}), flush=True)
+        print("RESULT " + json.dumps({"world": world, "tokens": win[:total].tolist(), "chunks": r.pf_chunks,
+                                      "launches": launches}), flush=True)
     r.close()
 shutdown()
