@@ -193,7 +193,8 @@ class GpuRunner:
         else:
             per = 5
         if self.piece.fp8:
-            per += 4                             # activation quantisers (QKV, O, gate/up, down inputs)
+            # activation quantisers (QKV, O, gate/up, down inputs); mxfp8 with fused epilogues keeps one per piece head
+            per += 0 if getattr(self.piece, "mx_fuse", False) else 4
         total = 1 + n * per                      # decode_advance + layers
         if per == 5 and not self.piece.fp8:
             total = 1 + self.piece.n_launches()  # sub-layer piece ends: count the GEMMs / attention actually present

@@ -175,3 +175,23 @@ def test_nat_api_is_inert_offline():
     r = nat.PortForwardingResult(True, "UPnP", "1.2.3.4", 4001)
     assert bool(r) and str(r) == "UPnP: 1.2.3.4:4001"
     assert nat.PortForwarder()._is_valid_ip("10.0.0.1") and not nat.PortForwarder()._is_valid_ip("nope")
+
+
+def test_mesh_staging_plan_sizes_quantised_hop_buffers():
+    """fp8 across the handoff: the hop slots for the e4m3 stream, its scale-factor chunks (tcgen05.cp layout: 512 B per
+    32-row tile and 128 K) and the sum-of-squares counters exist only for mxfp8 meshes; a gate/up | down cut adds the
+    e4m3 MLP hidden.  (Pure sizing logic -- the buffers themselves are cudaMalloc + IPC, tests/test_multigpu.py.)"""
+    import torch
+    from bee2bee_b200.parallel.mesh import MeshComm
+    m = MeshComm(0, 1, torch.device("cpu"), hidden=4096, max_tokens=512, groups=8, group_batch=32, hist_len=256)
+    assert not any(k in m._sizes() for k in ("stage_q", "stage_sf", "stage_ss", "stage_qh"))      # bf16 mesh: bf16 slots only
+    m = MeshComm(0, 1, torch.device("cpu"), hidden=4096, max_tokens=512, groups=8, group_batch=32, hist_len=256,
+                 ffn=14336, mx=True)
+    s = m._sizes()
+    assert s["stage_q"] == 8 * 32 * 4096 and s["stage_q_pf"] == 2 * 512 * 4096
+    assert s["stage_sf"] == 8 * (1 * 32 * 512) and s["stage_sf_pf"] == 2 * (16 * 32 * 512)
+    assert s["stage_ss"] == 8 * 32 * 4 and s["stage_ss_pf"] == 2 * 512 * 4
+    assert s["stage_qh"] == 8 * 32 * 14336 and s["stage_sfh_pf"] == 2 * (16 * 112 * 512)
+    assert all(v % 16 == 0 for k, v in s.items() if k.startswith("stage_sf")), "cp.async.bulk needs 16-byte aligned slots"
+    # a single-rank mesh has no endpoints at all
+    assert m.handoff(0).in_q == 0 and m.handoff_prefill(1).out_q == 0
