@@ -189,38 +189,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   constexpr uint32_t TCOLS = Cfg::kTmemCols;
 
   pdl_launch_dependents();
-  pdl_wait();                                               // the metadata below may come from an earlier kernel
-  const int seq = blockIdx.z, kvh = blockIdx.y;
-  const bool split_mode = p.splits > 1;
-  const int qblk = split_mode ? 0 : gridDim.x - 1 - blockIdx.x;   // longest (latest) query blocks first
-  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
-  const int q0 = qblk * QB;
-  if (q0 >= qlen) return;
-  const int nq_here = min(QB, qlen - q0);
-  const int qtok0 = p.q_start[seq] + q0;
-  const int pos0 = kvlen - qlen + q0;                       // absolute position of query 0 of this block
-  const int kv_hi = min(kvlen, pos0 + nq_here);
-  const int kv_lo = p.window > 0 ? max(0, pos0 - p.window + 1) : 0;
-  int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
-  if (split_mode) {
-    // this CTA's share of the key tiles (may be empty: it then publishes an empty partial, m = -inf, l = 0)
-    const int per = (t_hi - t_lo + p.splits - 1) / p.splits;
-    t_lo = min(t_hi, t_lo + static_cast<int>(blockIdx.x) * per);
-    t_hi = min(t_hi, t_lo + per);
-    if (t_hi <= t_lo) {
-      // empty share (short sequence, many splits): publish an empty partial and leave before any TMA / TMEM / barrier
-      // state exists (a CTA must not exit with a Q load in flight)
-      if (threadIdx.x < G) {
-        float* w = p.ws + (((static_cast<size_t>(seq) * p.n_kv + kvh) * p.splits + blockIdx.x) * p.ws_rows + threadIdx.x) * (D + 2);
-        for (int c = 0; c < D; ++c) w[c] = 0.f;
-        w[D] = -INFINITY;
-        w[D + 1] = 0.f;
-      }
-      return;
-    }
-  }
-  const int nt = t_hi - t_lo;
-
+  // ---- set-up that reads nothing an earlier kernel wrote (barriers, tensor memory, descriptor prefetch): under PDL the CTA
+  // is resident while the QKV GEMM still drains, so all of this is off the critical path; only then wait for the producer
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();             // the swizzled tiles need 1024-byte alignment
   uint8_t* q_s = smem;
@@ -256,7 +226,40 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  pdl_wait();                                               // q / K / V and the metadata below come from earlier kernels
+  const int seq = blockIdx.z, kvh = blockIdx.y;
+  const bool split_mode = p.splits > 1;
+  const int qblk = split_mode ? 0 : gridDim.x - 1 - blockIdx.x;   // longest (latest) query blocks first
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = qblk * QB;
+  bool active = q0 < qlen;                                  // CTA-uniform; an idle CTA only runs the tear-down below
+  const int nq_here = min(QB, qlen - q0);
+  const int qtok0 = p.q_start[seq] + q0;
+  const int pos0 = kvlen - qlen + q0;                       // absolute position of query 0 of this block
+  const int kv_hi = min(kvlen, pos0 + nq_here);
+  const int kv_lo = p.window > 0 ? max(0, pos0 - p.window + 1) : 0;
+  int t_lo = kv_lo / BKV, t_hi = (kv_hi + BKV - 1) / BKV;
+  if (active && split_mode) {
+    // this CTA's share of the key tiles (may be empty: it then publishes an empty partial, m = -inf, l = 0)
+    const int per = (t_hi - t_lo + p.splits - 1) / p.splits;
+    t_lo = min(t_hi, t_lo + static_cast<int>(blockIdx.x) * per);
+    t_hi = min(t_hi, t_lo + per);
+    if (t_hi <= t_lo) {
+      // empty share (short sequence, many splits): publish an empty partial; no TMA / MMA is ever issued by this CTA
+      if (threadIdx.x < G) {
+        float* w = p.ws + (((static_cast<size_t>(seq) * p.n_kv + kvh) * p.splits + blockIdx.x) * p.ws_rows + threadIdx.x) * (D + 2);
+        for (int c = 0; c < D; ++c) w[c] = 0.f;
+        w[D] = -INFINITY;
+        w[D + 1] = 0.f;
+      }
+      active = false;
+    }
+  }
+  const int nt = t_hi - t_lo;
+
+  if (!active) {
+    // nothing to compute (inactive row / empty split share)
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
