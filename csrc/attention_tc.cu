@@ -188,7 +188,6 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   constexpr uint32_t S_COL = 0, O_COL = 2 * BKV;
   constexpr uint32_t TCOLS = Cfg::kTmemCols;
 
-  pdl_launch_dependents();
   // ---- set-up that reads nothing an earlier kernel wrote (barriers, tensor memory, descriptor prefetch): under PDL the CTA
   // is resident while the QKV GEMM still drains, so all of this is off the critical path; only then wait for the producer
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -226,6 +225,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // dependents (the O-proj GEMM) may become resident from here on: every CTA of this grid already owns its tensor memory,
+  // so an early O-proj CTA that takes TMEM columns and then waits for this grid can never starve one of its CTAs
+  pdl_launch_dependents();
   pdl_wait();                                               // q / K / V and the metadata below come from earlier kernels
   const int seq = blockIdx.z, kvh = blockIdx.y;
   const bool split_mode = p.splits > 1;
