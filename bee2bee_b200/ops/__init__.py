@@ -119,18 +119,38 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
-def pick_prefill_tile(n_out: int, m_tok: int):
-    """(token tile, ring depth) of a prefill GEMM (m_tok > 64), measured on B200 (profiles/prefill_gemm.md): once a GEMM
-    has more tiles than SMs, TWO resident CTAs per SM with a shallow ring beat one CTA with a deep ring -- the epilogue
-    of one tile (TMEM -> registers -> global) overlaps the main loop of the other (955 vs 787 TFLOP/s over the
-    Llama-3-8B layer at 4096 tokens, 570 vs 551 at 512).  0 = the tile's default depth."""
-    tiles256 = (n_out // 128) * ((m_tok + 255) // 256)
-    tiles128 = (n_out // 128) * ((m_tok + 127) // 128)
+def pick_prefill_tile(n_out: int, m_tok: int, k: int = 0):
+    """(token tile, ring depth, cluster split-K) of a prefill GEMM (m_tok > 64), measured on B200 on the Llama-3-8B shapes
+    (profiles/prefill_gemm.md).  0 = the tile's default depth / let ``pick_splitk`` decide.
+
+    * more tiles than SMs: TWO resident CTAs per SM with a shallow ring beat one CTA with a deep ring -- the epilogue of
+      one tile (TMEM -> registers -> global) overlaps the main loop of the other (955 vs 787 TFLOP/s over the layer at
+      4096 tokens, 570 vs 551 at 512);
+    * fewer tiles than SMs (O-proj / down / QKV of a 256-1024 token chunk: 32-48 weight tiles): fill the machine with
+      split-K instead of running 2 waves of deep-ring CTAs.  Long K (down, 14336): 256-wide token tiles (the 128x256 MMA
+      runs at full rate, 128x128 does not), one CTA per SM, split-K until ~one CTA per SM (512 tokens: 66.9 vs 109.5 us).
+      Short K: 128-wide tiles with a 3-deep ring, two CTAs per SM, split-K until ~two CTAs per SM (O-proj, 512 tokens:
+      37.1 vs 55.7 us).  At least 32 k-blocks per CTA, split-K <= 4."""
+    tn = n_out // 128
+    tiles256 = tn * ((m_tok + 255) // 256)
+    tiles128 = tn * ((m_tok + 127) // 128)
     if m_tok > 256 and tiles256 > NUM_SMS:
-        return 256, 2
+        return 256, 2, 1
+    kb = k // 64
+
+    def split(tiles: int, cap: int) -> int:
+        s = 1
+        while s < 4 and tiles * s * 2 <= cap and kb // (s * 2) >= 32:
+            s *= 2
+        return s
+
+    if m_tok >= 256 and k >= 8192 and tiles256 <= NUM_SMS:
+        return 256, 0, split(tiles256, NUM_SMS)
     if tiles128 > NUM_SMS:
-        return 128, 3
-    return (128 if m_tok <= 512 else 256), 0
+        return 128, 3, 1
+    if m_tok >= 256 and k > 0:
+        return 128, 3, split(tiles128, 2 * NUM_SMS)
+    return (128 if m_tok <= 512 else 256), 0, 0          # small chunks: not measured, the decode heuristic decides
 
 
 #: cluster size of the TMA-multicast prefill GEMM (2 or 4); correct on hardware but NOT faster (the prefill GEMM is not
@@ -198,9 +218,14 @@ def gemm(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, *
         if sfa is not None:
             bn = pick_bn_mx(m_tok)
         elif m_tok > 64:
-            bn, st = pick_prefill_tile(n_out, m_tok)
+            bn, st, sk_hint = pick_prefill_tile(n_out, m_tok, k)
             if stages < 0:
                 stages = st
+            if splitk <= 0 and sk_hint > 0:
+                splitk = sk_hint
+                cap = native().gemm_max_splitk(bn, epi, max(stages, 0))      # reduce-scatter landing zone must fit the ring
+                while splitk > cap:
+                    splitk //= 2
         else:
             bn = pick_bn(m_tok)
     if stages < 0:

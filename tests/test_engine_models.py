@@ -304,6 +304,14 @@ def test_split_k_heuristic_matches_the_measured_optimum():
         assert pick(32, 32) == dict(qkv=4, o=4, gu=1, down=8, head=1)      # profiles/raw/layer_sweep_reduce_scatter.txt
         assert pick(16, 1) == dict(qkv=4, o=4, gu=1, down=4, head=1)       # >= 4 token columns per CTA of the cluster
         assert all(v == 1 for v in pick(256, 4096).values())               # prefill: tiles already fill the machine
+    # prefill chunks: (token tile, ring depth, split-K) per GEMM of a Llama-3-8B layer (profiles/prefill_gemm.md, split-K
+    # sweep): under-filled GEMMs are split along K until the machine is full instead of running two waves
+    tile = lambda m: {k: ops.pick_prefill_tile(n, m, kk) for k, (n, kk) in shapes.items() if k != "head"}
+    assert tile(512) == dict(qkv=(128, 3, 1), o=(128, 3, 2), gu=(256, 2, 1), down=(256, 0, 2))
+    assert tile(256) == dict(qkv=(128, 3, 2), o=(128, 3, 2), gu=(128, 3, 1), down=(256, 0, 4))
+    assert tile(1024) == dict(qkv=(256, 2, 1), o=(128, 3, 1), gu=(256, 2, 1), down=(256, 0, 1))
+    assert all(v == (256, 2, 1) for v in tile(4096).values())
+    assert ops.pick_prefill_tile(256, 512, 256) == (128, 3, 1)             # tiny models: too few k-blocks to split
 
 
 def test_weights_policy_random_init_is_opt_in(monkeypatch, tmp_path):

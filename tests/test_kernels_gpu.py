@@ -52,6 +52,22 @@ def test_gemm_splitk_cluster(splitk, m):
     close(ops.gemm(w, x, splitk=splitk), x.float() @ w.float().t())       # cluster / DSMEM kernel
 
 
+@pytest.mark.parametrize("bn,splitk,stages", [(256, 2, 0), (256, 4, 0), (128, 2, 3), (128, 4, 3), (128, 2, 0)])
+@pytest.mark.parametrize("m", [256, 300, 512])
+def test_gemm_prefill_splitk_tiles(bn, splitk, stages, m):
+    """the (token tile, split-K, ring depth) combinations ops.pick_prefill_tile emits for under-filled prefill GEMMs:
+    cluster split-K with the DSMEM reduce-scatter on 128 / 256-wide token tiles, plain and residual epilogues, ragged
+    last token tile"""
+    w, x, r = bf(512, 4096, scale=0.03), bf(m, 4096), bf(m, 512)
+    ref = x.float() @ w.float().t()
+    close(ops.gemm(w, x, bn=bn, splitk=splitk, stages=stages), ref)
+    out = ops.gemm(w, x, bn=bn, splitk=splitk, stages=stages, epi=ops.EPI_RESIDUAL, residual=r)
+    close(out, ref + r.float())
+    # ... and through the heuristic itself (long K -> 256-wide tiles + split-K)
+    w2, x2 = bf(256, 8192, scale=0.02), bf(m, 8192)
+    close(ops.gemm(w2, x2), x2.float() @ w2.float().t())
+
+
 def test_gemm_fp32_out_and_bias():
     w, x = bf(256, 256, scale=0.05), bf(7, 256)
     bias = torch.randn(256, device="cuda")
