@@ -119,6 +119,10 @@ def pick_bn(m_tok: int) -> int:
     return 256 if m_tok > 512 else 128
 
 
+#: 0 restores the round-2 mid-term rule for under-filled prefill GEMMs (128-wide tiles, deep ring, decode split-K heuristic)
+PREFILL_SPLITK = os.environ.get("B2B_PREFILL_SPLITK", "1") == "1"
+
+
 def pick_prefill_tile(n_out: int, m_tok: int, k: int = 0):
     """(token tile, ring depth, cluster split-K) of a prefill GEMM (m_tok > 64), measured on B200 on the Llama-3-8B shapes
     (profiles/prefill_gemm.md).  0 = the tile's default depth / let ``pick_splitk`` decide.
@@ -144,11 +148,11 @@ def pick_prefill_tile(n_out: int, m_tok: int, k: int = 0):
             s *= 2
         return s
 
-    if m_tok >= 256 and k >= 8192 and tiles256 <= NUM_SMS:
+    if PREFILL_SPLITK and m_tok >= 256 and k >= 8192 and tiles256 <= NUM_SMS:
         return 256, 0, split(tiles256, NUM_SMS)
     if tiles128 > NUM_SMS:
         return 128, 3, 1
-    if m_tok >= 256 and k > 0:
+    if PREFILL_SPLITK and m_tok >= 256 and k > 0:
         return 128, 3, split(tiles128, 2 * NUM_SMS)
     return (128 if m_tok <= 512 else 256), 0, 0          # small chunks: not measured, the decode heuristic decides
 
