@@ -43,6 +43,7 @@ class PageAllocator:
         self._key_of: Dict[int, bytes] = {}                           # cached page -> prefix key
         self._page_of: Dict[bytes, int] = {}                          # prefix key -> page
         self._lru: "OrderedDict[int, None]" = OrderedDict()           # cached pages nobody owns (evictable), oldest first
+        self._cached: Dict[int, int] = {}                             # owner -> prompt tokens served from the cache
         self.hit_tokens = 0
         self.lookup_tokens = 0
 
@@ -100,7 +101,6 @@ class PageAllocator:
             self._ref[p] = 1
         pages = matched + fresh
         self._owned.setdefault(owner, []).extend(pages)
-        self._cached = getattr(self, "_cached", {})
         self._cached[owner] = len(matched) * PAGE
         if prompt is not None:
             self.lookup_tokens += len(prompt)
@@ -108,7 +108,7 @@ class PageAllocator:
         return pages
 
     def cached_tokens(self, owner: int) -> int:
-        return getattr(self, "_cached", {}).get(owner, 0)
+        return self._cached.get(owner, 0)
 
     def commit(self, owner: int, prompt: Sequence[int]) -> None:
         """Register the full prompt pages of ``owner`` as shareable (their KV is written by the prefill that is enqueued
@@ -134,7 +134,7 @@ class PageAllocator:
                 self._lru.move_to_end(p)
             else:
                 self._free.append(p)
-        getattr(self, "_cached", {}).pop(owner, None)
+        self._cached.pop(owner, None)
 
     def invalidate(self, owner: int) -> None:
         """The KV content of ``owner``'s pages cannot be trusted (its prefill failed): forget their prefix keys."""
