@@ -13,6 +13,7 @@ Backends: ``GpuRunner`` (hand-written sm_100a kernels; one per GPU, pieces over 
 from __future__ import annotations
 
 import itertools
+import os
 import collections
 import queue
 import statistics
@@ -39,6 +40,8 @@ class SamplingParams:
     seed: Optional[int] = None
     stop_token_ids: Sequence[int] = ()
     ignore_eos: bool = False
+    timeout_s: Optional[float] = None  # deadline from submission; an overdue request is retired ("timeout") at the next
+                                       # burst boundary and frees its slot + pages (default: B2B_REQUEST_TIMEOUT_S, 0 = none)
 
 
 @dataclass
@@ -205,6 +208,7 @@ class Engine:
         self._wake = threading.Event()
         self._stop = False
         self.broken: Optional[str] = None          # set once the mesh aborted (MeshStalled): the engine refuses new work
+        self.default_timeout_s = float(os.environ.get("B2B_REQUEST_TIMEOUT_S", "0") or 0)   # 0 = requests have no deadline
         self._thread: Optional[threading.Thread] = None
         self.host_ms = {"prefill": 0.0, "decode": 0.0, "collect": 0.0}     # host wall time per scheduler phase
         self._ttfts: "collections.deque[float]" = collections.deque(maxlen=4096)   # submit -> first token, ms
@@ -379,6 +383,7 @@ class Engine:
                 fresh.append(self._waiting.get_nowait())
             except queue.Empty:
                 break
+        self._expire_overdue()
         with self._lock:
             cancelled, self._cancelled = self._cancelled, []
         if self.world > 1 and self.plan_sync:
@@ -449,6 +454,19 @@ class Engine:
         self.host_ms["collect"] += (time.perf_counter() - tc) * 1e3
         self.stats["busy_s"] += time.time() - t0
         return True
+
+    def _expire_overdue(self) -> None:
+        """Deadline check (rank 0 / single rank decides; the cancellation then travels with the plan like any other):
+        queued and running requests whose ``timeout_s`` has passed are cancelled with finish_reason "timeout"."""
+        if self.rank != 0 or (self.world > 1 and not self.plan_sync):
+            return          # replicated (SPMD) submission without a plan broadcast: a wall-clock decision would diverge
+        now = time.time()
+        for r in list(self._pending) + list(self._running.values()):
+            limit = r.params.timeout_s if r.params.timeout_s is not None else self.default_timeout_s
+            if limit and limit > 0 and not r.cancelled and now - r.t_submit > limit:
+                r.finish_reason = "timeout"
+                self.cancel(r, "timeout")
+                self.stats["timeouts"] = self.stats.get("timeouts", 0) + 1
 
     def _retire_cancelled(self, rids) -> None:
         """Burst boundary (the device is idle): drop cancelled requests from the queue / free their slot + pages."""

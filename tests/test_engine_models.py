@@ -398,3 +398,29 @@ def test_prefix_cache_allocator_shares_pins_and_evicts():
     d = PageAllocator(10, prefix_cache=False)
     d.allocate(1, 192, q); d.commit(1, q); d.release(1); d.allocate(2, 192, q)
     assert d.cached_tokens(2) == 0
+
+
+def test_request_deadline_frees_slot_and_pages():
+    """'timeout -> slot + pages freed at the next burst boundary'.  A request past its ``timeout_s`` is
+    retired with finish_reason "timeout" whether it is still queued or already decoding; the others are unaffected."""
+    import time
+    eng = Engine("tiny-llama", device="cpu", max_batch=1, max_seq_len=256, decode_burst=2)
+    slow = eng.submit([1, 2, 3], SamplingParams(max_new_tokens=200, temperature=0.0, ignore_eos=True, timeout_s=0.05))
+    queued = eng.submit([4, 5], SamplingParams(max_new_tokens=200, temperature=0.0, ignore_eos=True, timeout_s=0.05))
+    ok = eng.submit([6, 7], SamplingParams(max_new_tokens=3, temperature=0.0, ignore_eos=True))
+    eng.step()
+    assert not slow.done.is_set() and len(slow.out_ids) >= 1
+    time.sleep(0.08)
+    while not ok.done.is_set():
+        eng.step()
+    assert slow.finish_reason == "timeout" and queued.finish_reason == "timeout" and not queued.out_ids
+    assert len(slow.out_ids) < 200 and len(ok.out_ids) == 3 and ok.finish_reason == "length"
+    assert eng.alloc.free_pages == eng.alloc.num_pages - 1 and len(eng._free_slots) == 1
+    assert eng.metrics().get("timeouts", eng.stats.get("timeouts")) == 2
+    # engine-wide default deadline
+    eng.default_timeout_s = 0.01
+    r = eng.submit([1], SamplingParams(max_new_tokens=500, temperature=0.0, ignore_eos=True))
+    eng.step()
+    time.sleep(0.03)
+    eng.step()
+    assert r.done.is_set() and r.finish_reason == "timeout"
