@@ -290,7 +290,8 @@ class Engine:
                 "prefill_tokens": self.stats["prefill_tokens"], "decode_steps": self.stats["steps"],
                 "tokens_per_s": self.stats["tokens"] / busy, "running": len(self._running),
                 "waiting": self._waiting.qsize() + len(self._pending), "kv_utilization": self.alloc.utilization(),
-                "healthy": self.broken is None, "prefix_cache": self.alloc.cache_stats(),
+                "healthy": self.broken is None, "cancelled": self.stats.get("cancelled", 0),
+                "timeouts": self.stats.get("timeouts", 0), "prefix_cache": self.alloc.cache_stats(),
                 "prefix_cache_hit_tokens": self.stats.get("prefix_cache_hit_tokens", 0), "uptime_s": up, "h2d_bytes": self.h2d_bytes + getattr(self.runner, "h2d_bytes", 0),
                 "d2h_bytes": self.d2h_bytes, "native_launches": getattr(self.runner, "kernel_launches", 0),
                 "host_ms": dict(self.host_ms),

@@ -416,7 +416,7 @@ def test_request_deadline_frees_slot_and_pages():
     assert slow.finish_reason == "timeout" and queued.finish_reason == "timeout" and not queued.out_ids
     assert len(slow.out_ids) < 200 and len(ok.out_ids) == 3 and ok.finish_reason == "length"
     assert eng.alloc.free_pages == eng.alloc.num_pages - 1 and len(eng._free_slots) == 1
-    assert eng.metrics().get("timeouts", eng.stats.get("timeouts")) == 2
+    assert eng.metrics()["timeouts"] == 2 and eng.metrics()["cancelled"] >= 1
     # engine-wide default deadline
     eng.default_timeout_s = 0.01
     r = eng.submit([1], SamplingParams(max_new_tokens=500, temperature=0.0, ignore_eos=True))
