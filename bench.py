@@ -260,6 +260,18 @@ def run_ours(args):
                "h2d_bytes_per_step": (eng.h2d_bytes + runner.h2d_bytes - h0) / K,
                "d2h_bytes_per_step": eng.d2h_bytes / K, "includes": "prefill+decode, scheduler, token readback",
                "host_ms": dict(eng.host_ms)}
+        # rank-count independence: greedy continuation of the same prompts through the same public call;
+        # the checksum over the first 32 sequences must be identical at every N (the pieces only change the transport:
+        # same kernels, same tiles, same split-K -- tests/test_multigpu.py asserts it token for token on 2 / 4 / 8 GPUs)
+        try:
+            import zlib
+            gouts = eng.generate(prompts, SamplingParams(max_new_tokens=8, temperature=0.0, top_p=1.0,
+                                                         repetition_penalty=1.0, ignore_eos=True))
+            flat = [int(t) for o in gouts[:32] for t in o]
+            e2e["greedy_check"] = {"crc32_first_32_seqs_x_8_tokens": zlib.crc32(",".join(map(str, flat)).encode()),
+                                   "seq0": [int(t) for t in gouts[0][:8]]}
+        except Exception as exc:        # never let the consistency probe take the measurement down
+            e2e["greedy_check"] = {"error": repr(exc)[:200]}
 
     if rank == 0:
         peaks = measured_peaks()
