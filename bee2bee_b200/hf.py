@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import queue
 import threading
-from typing import Any, Dict, Iterator, List, Optional, Tuple
+from typing import Any, Dict, Iterator, Optional, Tuple
 
 from .engine.core import Engine, SamplingParams
 from .engine.tokenizer import STOP_WORDS, cut_at_stop_words, load_tokenizer, parse_transcript

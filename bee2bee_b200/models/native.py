@@ -18,9 +18,9 @@ of the reference (/root/reference/bee2bee/hf.py:180-205, bee2bee/node.py:249-277
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 import os
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, Iterable, Optional
 
 import torch
 

@@ -8,8 +8,7 @@ the Hugging Face modelling code the reference delegates to
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, Optional, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -12,7 +12,7 @@ import ipaddress
 import socket
 import struct
 import time
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 from .stun_client import STUNClient
 from .utils import get_lan_ip, offline

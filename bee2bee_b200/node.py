@@ -153,7 +153,7 @@ class TaskExecutor:
 
     # ---- partitioned model: layer range [start, end) ------------------------------------------
     def _t_hf_part_load(self, p):
-        from .models.config import resolve_config, supports_half_layer_pieces
+        from .models.config import resolve_config
 
         name = p.get("model_name", "distilgpt2")
         cfg = resolve_config(name)

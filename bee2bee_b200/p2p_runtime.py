@@ -23,7 +23,7 @@ import time
 from typing import Any, Awaitable, Callable, Dict, List, Optional, Tuple
 
 from . import protocol as P
-from .dht import DHTNode, announce_piece, find_providers
+from .dht import DHTNode, announce_piece
 from .p2p import generate_join_link, parse_join_link, registration_url, sha256_hex_bytes
 from .pieces import LayerPiece, piece_hashes, split_pieces, verify_and_reassemble
 from .registry import RegistryClient

@@ -21,7 +21,6 @@ import threading
 import time
 from typing import Any, Dict, Iterator, List, Optional
 
-import numpy as np
 import torch
 
 from ..engine.tokenizer import STOP_WORDS, cut_at_stop_words, load_tokenizer, parse_transcript

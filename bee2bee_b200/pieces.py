@@ -12,11 +12,10 @@
 """
 from __future__ import annotations
 
-import io
 import json
 import os
-from dataclasses import asdict, dataclass, field
-from typing import Dict, Iterable, List, Optional, Sequence
+from dataclasses import asdict, dataclass
+from typing import Dict, List, Optional, Sequence
 
 from .p2p import chunk_bytes, sha256_hex_bytes
 

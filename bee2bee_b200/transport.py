@@ -12,7 +12,7 @@ The token path never touches a transport: activations move GPU->GPU through
 from __future__ import annotations
 
 import asyncio
-from typing import Any, AsyncIterator, Awaitable, Callable, Dict, Optional, Tuple
+from typing import AsyncIterator, Awaitable, Callable, Dict, Optional
 
 MAX_FRAME = 32 * 1024 * 1024
 
