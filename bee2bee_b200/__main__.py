@@ -80,10 +80,14 @@ def serve_ollama(model, host, port, public_host, region, api_port, pieces, rando
 @click.option("--max-seq-len", default=None, type=int, help="context budget per sequence")
 @click.option("--random-weights", is_flag=True, help="allow random-init weights when --model is not a local checkpoint "
                                                      "directory (benchmarks / smoke tests: the node serves noise)")
-def serve_hf(model, port, region, api_port, pieces, max_batch, max_seq_len, random_weights):
+@click.option("--supervised", is_flag=True, help="run the engine (one worker process per GPU piece) as a restartable child "
+                                                 "group: a dead rank is replaced without restarting this node")
+def serve_hf(model, port, region, api_port, pieces, max_batch, max_seq_len, random_weights, supervised):
     """Serve a Hugging Face model on the native engine with built-in FastAPI."""
     if random_weights:
         os.environ["B2B_ALLOW_RANDOM_WEIGHTS"] = "1"      # inherited by the follower ranks of --pieces N
+    if supervised:
+        os.environ["B2B_SUPERVISED"] = "1"                # hf.load_model_and_tokenizer puts the engine behind the supervisor
     kw = {}
     if max_batch:
         kw["max_batch"] = max_batch

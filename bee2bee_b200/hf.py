@@ -54,7 +54,7 @@ class LoadedModel:
         self.engine.close()
 
 
-_MODELS: Dict[Tuple[str, str, int], LoadedModel] = {}
+_MODELS: Dict[Tuple[str, str, int, bool], LoadedModel] = {}
 _LOCK = threading.Lock()
 
 
@@ -66,12 +66,23 @@ def load_model_and_tokenizer(model_name: str, device: Optional[str] = None, piec
 
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
-    key = (model_name, str(device), int(pieces))
+    import os
+
+    supervised = os.environ.get("B2B_SUPERVISED", "0") == "1"
+    key = (model_name, str(device), int(pieces), supervised)
     with _LOCK:
         lm = _MODELS.get(key)
         if lm is None:
             cfg = resolve_config(model_name)
-            if pieces > 1 and str(device).startswith("cuda"):
+            if supervised:
+                # the engine (one worker process per GPU piece, or one CPU worker) runs as a restartable child group;
+                # this process never owns a CUDA context, so a dead rank cannot take the serving front down
+                from .parallel.supervisor import SupervisedEngine
+
+                gpu_mesh = pieces > 1 and str(device).startswith("cuda")
+                kw = dict(engine_kw) if gpu_mesh else dict(engine_kw, pieces=pieces)
+                eng = SupervisedEngine(model_name, device=str(device), world=pieces if gpu_mesh else 1, engine_kw=kw)
+            elif pieces > 1 and str(device).startswith("cuda"):
                 # one process per GPU: this process becomes rank 0, followers are spawned
                 from .parallel.launch import build_engine, spawn_followers
 
