@@ -116,8 +116,11 @@ class SupervisedEngine:
     # ------------------------------------------------------------------ group life cycle
     def _spawn(self) -> None:
         port = _free_port()
+        # the workers import this package by name whatever the front's working directory is
+        pkg_parent = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        pypath = pkg_parent + (os.pathsep + os.environ["PYTHONPATH"] if os.environ.get("PYTHONPATH") else "")
         base = dict(os.environ, B2B_SUP_TOKEN=self._token, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                    WORLD_SIZE=str(self.world))
+                    WORLD_SIZE=str(self.world), PYTHONPATH=pypath)
         self._procs = []
         for r in range(self.world):
             env = dict(base, RANK=str(r), LOCAL_RANK=str(r))
