@@ -15,7 +15,11 @@ python -m pytest tests/test_multigpu.py -x -q -m gpu -k "eight or four" 2>&1 | t
 run ours_n8 8 --steps 20 --warmup 5
 run ours_n4 4 --steps 20 --warmup 5
 run cfg3_ours_n8 8 --config 3 --steps 20 --warmup 5
+# rank-count independence: the greedy checksum of the bench line must be the same at every N
+python bench.py --steps 8 --warmup 3 > $OUT/ours_n1.log 2>&1
+grep -ho '"greedy_check": {[^}]*}' $OUT/ours_n1.log $OUT/ours_n4.log $OUT/ours_n8.log
 if [ "${1:-}" = "full" ]; then
+  B2B_MX_HANDOFF=0 run cfg3_ours_n8_bf16hop 8 --config 3 --steps 20 --warmup 5      # A/B of the quantised hop
   run nccl_n8 8 --steps 20 --warmup 5 --impl nccl
   run cfg2_ours_n8 8 --config 2 --steps 64 --warmup 8
   run cfg2_nccl_n8 8 --config 2 --steps 64 --warmup 8 --impl nccl --no-e2e
