@@ -16,6 +16,7 @@ os.environ.setdefault("B2B_ALLOW_RANDOM_WEIGHTS", "1")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout; inert without the plugin)")
 
 
 def pytest_collection_modifyitems(config, items):
