@@ -149,8 +149,7 @@ async def connect_peer(addr: str) -> Dict[str, Any]:
         return {"status": "error", "message": str(exc)}
 
 
-@app.get("/metrics", dependencies=[Depends(get_api_key)])
-def metrics() -> Dict[str, Any]:
+def _engine_metrics() -> Dict[str, Any]:
     out: Dict[str, Any] = {}
     if node is None:
         return out
@@ -159,6 +158,37 @@ def metrics() -> Dict[str, Any]:
         if eng is not None:
             out[name] = eng.metrics()
     return out
+
+
+def prometheus_text(per_service: Dict[str, Any]) -> str:
+    """Engine counters in the Prometheus text exposition format (scalars only; nested dicts are flattened with '_')."""
+    lines = []
+
+    def emit(service: str, key: str, val) -> None:
+        if isinstance(val, bool):
+            val = int(val)
+        if isinstance(val, (int, float)):
+            name = "bee2bee_" + "".join(c if c.isalnum() else "_" for c in key)
+            lines.append(f'{name}{{service="{service}"}} {float(val):.6g}')
+        elif isinstance(val, dict):
+            for k, v in val.items():
+                emit(service, f"{key}_{k}", v)
+
+    for service, m in per_service.items():
+        for key, val in m.items():
+            if key != "trace":
+                emit(service, key, val)
+    return "\n".join(lines) + "\n"
+
+
+@app.get("/metrics", dependencies=[Depends(get_api_key)])
+def metrics(format: Optional[str] = None):
+    """Engine counters per local service (JSON); ``?format=prometheus`` for the text exposition format."""
+    data = _engine_metrics()
+    if format == "prometheus":
+        from fastapi.responses import PlainTextResponse
+        return PlainTextResponse(prometheus_text(data), media_type="text/plain; version=0.0.4")
+    return data
 
 
 @app.get("/topology", dependencies=[Depends(get_api_key)])

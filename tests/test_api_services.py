@@ -63,6 +63,14 @@ def test_chat_local_service_buffered_and_streaming(client):
     # errors are HTTP 200 with status=error (reference contract)
     r = client.post("/generate", json={"prompt": "x", "model": "no-such-model"})
     assert r.status_code == 200 and r.json()["status"] == "error"
+    # engine counters: JSON per service, and the Prometheus text exposition format
+    m = client.get("/metrics").json()["hf"]
+    assert m["requests"] >= 3 and m["tokens_generated"] >= 13 and m["healthy"] is True and m["timeouts"] == 0
+    prom = client.get("/metrics", params={"format": "prometheus"})
+    assert prom.headers["content-type"].startswith("text/plain")
+    rows = dict(l.rsplit(" ", 1) for l in prom.text.strip().splitlines())
+    assert float(rows['bee2bee_requests{service="hf"}']) == m["requests"]
+    assert float(rows['bee2bee_healthy{service="hf"}']) == 1.0 and 'bee2bee_prefix_cache_hit_rate{service="hf"}' in rows
     svc.model.engine.stop()
 
 
