@@ -208,8 +208,10 @@ def config_cmd(key, value):
 
 
 @cli.command()
-def topology():
-    """Print the local NVLink topology table (devices, peer access)."""
+@click.option("--model", default=None, help="also print how this model (preset / alias / local directory) is cut into pieces")
+@click.option("--pieces", default=0, type=int, help="number of pieces (GPUs) for --model; default: the GPUs of this box")
+def topology(model, pieces):
+    """Print the local NVLink topology table (devices, peer access) and, with --model, the piece plan."""
     import torch
 
     n = torch.cuda.device_count() if torch.cuda.is_available() else 0
@@ -219,6 +221,19 @@ def topology():
 
         C = ops.native()
         out["can_access_peer"] = [[bool(i == j or C.can_access_peer(i, j)) for j in range(n)] for i in range(n)]
+    if model:
+        from .models.config import UNITS_PER_LAYER, piece_units, resolve_config, unit_layers
+
+        cfg = resolve_config(model)
+        kinds = ("attention block (QKV, attention, O-proj)", "gate/up GEMM", "down GEMM")
+        plan = piece_units(cfg, pieces or max(1, n))
+        out["model"] = {"name": cfg.name, "layers": cfg.n_layers, "hidden": cfg.hidden_size, "ffn": cfg.ffn_size,
+                        "vocab": cfg.vocab_size}
+        out["pieces"] = [{"piece": i, "units": [u0, u1], "n_units": u1 - u0,
+                          "layers": [min(unit_layers((u0, u1))), max(unit_layers((u0, u1)))],
+                          "head_gemm_of": kinds[u0 % UNITS_PER_LAYER], "tail_gemm_of": kinds[(u1 - 1) % UNITS_PER_LAYER],
+                          "extras": (["embedding"] if i == 0 else []) + (["lm_head", "sampler"] if i == len(plan) - 1 else [])}
+                         for i, (u0, u1) in enumerate(plan)]
     click.echo(json.dumps(out, indent=2))
 
 

@@ -209,3 +209,19 @@ def test_cli_surface(monkeypatch):
     res = r.invoke(cli, ["config", "bootstrap_url", "ws://1.2.3.4:5"])
     assert res.exit_code == 0
     assert json.loads(r.invoke(cli, ["config"]).output)["bootstrap_url"] == "ws://1.2.3.4:5"
+
+
+def test_cli_topology_prints_the_piece_plan():
+    from click.testing import CliRunner
+
+    from bee2bee_b200.__main__ import cli
+
+    r = CliRunner()
+    assert "--supervised" in r.invoke(cli, ["serve-hf", "--help"]).output
+    res = r.invoke(cli, ["topology", "--model", "llama-3-8b", "--pieces", "8"])
+    assert res.exit_code == 0, res.output
+    d = json.loads(res.output)
+    assert [p["n_units"] for p in d["pieces"]] == [12, 12, 13, 13, 13, 13, 13, 7]      # thirds of a layer, lm_head on the last
+    assert d["pieces"][0]["extras"] == ["embedding"] and d["pieces"][-1]["extras"] == ["lm_head", "sampler"]
+    assert d["pieces"][2]["layers"] == [8, 12] and d["pieces"][2]["tail_gemm_of"].startswith("attention block")
+    assert d["model"]["layers"] == 32 and "can_access_peer" in d
