@@ -12,7 +12,7 @@ from bee2bee_b200.engine.core import SamplingParams
 from bee2bee_b200.parallel.supervisor import SupervisedEngine
 
 
-@pytest.mark.timeout(240)
+@pytest.mark.timeout(900)
 def test_supervised_engine_survives_a_killed_worker():
     sup = SupervisedEngine("tiny-llama", device="cpu", world=1, engine_kw=dict(max_batch=2, max_seq_len=2048))
     try:
